@@ -1,0 +1,191 @@
+/* octane_b200.h -- C ABI of the B200-native OCTANE dense variational
+ * optical-flow path (liboctane_b200.so).
+ *
+ * Plain C: pointers, sizes and POD structs only; no C++ / torch types.  Every
+ * entry point returns 0 on success and a negative OCTANE_E* code on failure
+ * (the reference prints and exit()s, or ignores CUDA errors:
+ * src/oct_variational_optical_flow.cu:1255-1266,1421,1431); nothing here ever
+ * calls exit().  There is NO CPU fallback: without a CUDA device every compute
+ * entry point fails with OCTANE_ENODEV.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   octane_variational_flow*   void oct_variational_optical_flow(Image,Image,float*CTH,
+ *                              float*u,float*v,int nx,int ny,int nc,OFFlags)
+ *                              src/oct_variational_optical_flow.cu:1213
+ *   octane_pix2uv*             void oct_pix2uv_cuda(GOESVar&,double t2,float*u,float*v,
+ *                              short*ur,short*vr,short*ur2,short*vr2,OFFlags)
+ *                              src/oct_pix2uv_cuda.cu:265
+ *   octane_optical_flow        int oct_optical_flow(GOESVar&,GOESVar&,OFFlags&)
+ *                              src/oct_optical_flow.cc:21 (variational branch + CTP pack + navigation)
+ *   octane_params              the OFFlags fields the path reads, include/offlags.h:4-72
+ *                              (src/oct_variational_optical_flow.cu:1229-1241,
+ *                               src/oct_pix2uv_cuda.cu:279,291-297)
+ *   octane_nav                 GOESNAVVar, include/goesread.h:3-14 (fields read by
+ *                              src/oct_pix2uv_cuda.cu:27-172,295)
+ * Image layout everywhere: row-major float32, index i + nx*j (+ nx*ny*c), i = x
+ * (fastest), as the reference (src/oct_variational_optical_flow.cu:316-320).
+ */
+#ifndef OCTANE_B200_H
+#define OCTANE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCTANE_ABI_VERSION 1
+
+enum {
+    OCTANE_OK = 0,
+    OCTANE_ENODEV = -1,   /* no CUDA device (reference: prints + exit(0)) */
+    OCTANE_EINVAL = -2,   /* bad argument */
+    OCTANE_ENOMEM = -3,   /* device allocation failed */
+    OCTANE_ECUDA = -4,    /* CUDA runtime error (octane_last_error has the text) */
+    OCTANE_EHALO = -5,    /* banded run: a warp left the band's halo (raise max_disp) */
+    OCTANE_ECOMM = -6     /* NCCL missing or failed */
+};
+
+/* OFFlags subset.  Defaults = src/main.cc:53-108. */
+typedef struct octane_params {
+    double alpha;      /* -alpha   smoothness weight            (5)   */
+    double lambda;     /* -lambda  gradient-constancy weight    (1)   */
+    double lambdac;    /* -lambdac first-guess hinting weight   (0)   */
+    double scaleF;     /* pyramid scale factor                  (0.5) */
+    double scsig;      /* deprecated, carried for layout parity (400) */
+    int kiters;        /* -kiters  pyramid levels               (4)   */
+    int liters;        /* -liters  inner iterations per GNC step(3)   */
+    int cgiters;       /* PCG iteration cap                     (30)  */
+    int dozim;         /* Zimmer normalisation, 0 with -brox    (1)   */
+    int setdevice;     /* 0-based CUDA device                   (0)   */
+    int pixuv;         /* -pd: U,V = 100*pixel displacement     (0)   */
+    int dopolar;       /* -Polar                                (0)   */
+    int domerc;        /* -Merc                                 (0)   */
+    int first_guess;   /* 1: u/v inputs hold a first guess (reference semantics of the
+                          in/out arrays); 0: start from zero without reading them,
+                          which is what oct_optical_flow.cc:38-48 feeds the solver */
+    int max_disp;      /* banded (multi-GPU) runs: bound on |v| in full-res pixels that
+                          sizes the image-2 warp halo                (64) */
+    int doCTH;         /* -i1cth: pack CTP                      (0)   */
+    int ir;            /* -ir: CTP = (CTH-300)*100              (0)   */
+} octane_params;
+
+/* GOESNAVVar subset (double/float split as in the reference: the float fields
+ * take part in float arithmetic, src/oct_pix2uv_cuda.cu:40-41,99-100). */
+typedef struct octane_nav {
+    double pph, req, rpol, lam0;
+    float xScale, xOffset, yScale, yOffset;
+    float g2xOffset, g2yOffset;          /* file-2 offsets: sector-moved guard, :295 */
+    float lat1, lon1, lon0, R;           /* polar / Mercator constants */
+    int minX, minY;                      /* sector origin added to the pixel index, :192 */
+} octane_nav;
+
+/* Per-call statistics (filled by the last solve on the context). */
+#define OCTANE_MAX_SOLVES 256
+typedef struct octane_stats {
+    int n_levels;
+    int n_solves;                         /* kiters*3*liters */
+    int level_nx[16], level_ny[16];
+    int cg_iterations[OCTANE_MAX_SOLVES]; /* PCG iterations actually executed per solve */
+    long long kernel_launches;            /* our kernels launched by the last call */
+    double algorithmic_bytes;             /* sum_k N_k(100+3*liters*80) + 124*sum n_it*N_k */
+    /* profile mode (octane_ctx_set_profile): CUDA-event timings on our stream */
+    double ms_total;                      /* whole call, device side */
+    double ms_pyramid, ms_build, ms_pcg_pass1, ms_pcg_pass2, ms_update, ms_nav;
+    long long n_pcg_pass1, n_pcg_pass2;   /* launches that did work (not early-exited) */
+    double finest_pass1_ms, finest_pass2_ms;   /* average per working launch, finest level */
+    long long finest_pixels;              /* pixels one finest-level launch covers on this rank */
+} octane_stats;
+
+typedef struct octane_ctx octane_ctx;
+
+/* library / device */
+int         octane_abi_version(void);
+const char* octane_last_error(void);
+int         octane_device_count(void);
+void        octane_params_default(octane_params* p);
+
+/* A context owns a CUDA stream and a reusable device workspace (the reference
+ * allocates and frees 37 managed buffers per call, :1268-1328,1441-1472). */
+int  octane_ctx_create(octane_ctx** ctx, int device);
+void octane_ctx_destroy(octane_ctx* ctx);
+int  octane_ctx_set_profile(octane_ctx* ctx, int on);      /* per-stage CUDA-event timing */
+int  octane_ctx_set_graphs(octane_ctx* ctx, int on);       /* CUDA-graph the PCG loop (default on) */
+int  octane_get_stats(octane_ctx* ctx, octane_stats* out);
+int  octane_ctx_synchronize(octane_ctx* ctx);
+size_t octane_workspace_bytes(int nx, int ny, int nc, const octane_params* p);
+
+/* Pyramid geometry: level k has factor scaleF^(kiters-1-k) and size
+ * (int)(n*factor+0.5) (src/oct_variational_optical_flow.cu:50-54,488-489). */
+int octane_level_dims(int nx, int ny, const octane_params* p, int k, int* xi, int* yi);
+
+/* ---- host-buffer entry points (blocking; copies inside) ---------------- */
+
+/* u,v: in = first guess if p->first_guess, out = flow in pixels. */
+int octane_variational_flow(octane_ctx* ctx, const float* img1, const float* img2,
+                            int nx, int ny, int nc, const octane_params* p,
+                            float* u_inout, float* v_inout);
+
+/* U,V = (short)(100*m/s) (or 100*pixels with pixuv); U_raw,V_raw = (short)(100*pixels).
+ * Returns 1 (not an error) when the sector-moved guard zeroed the outputs. */
+int octane_pix2uv(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
+                  const float* u, const float* v, int nx, int ny, const octane_params* p,
+                  short* U, short* V, short* U_raw, short* V_raw, float* dT);
+
+/* Dispatcher: solve + CTP pack + navigation with the flow kept on the device
+ * between the two stages.  cth/ctp may be NULL when !p->doCTH. */
+int octane_optical_flow(octane_ctx* ctx, const float* img1, const float* img2, const float* cth,
+                        int nx, int ny, int nc, const octane_nav* nav, double t1, double t2,
+                        const octane_params* p, float* upix_inout, float* vpix_inout,
+                        short* U, short* V, short* U_raw, short* V_raw, short* ctp, float* dT);
+
+/* ---- device-pointer entry points (stream-ordered on the ctx stream) ----- */
+/* All pointers are device memory on the context's device, dense (stride nx). */
+int octane_variational_flow_dev(octane_ctx* ctx, const float* d_img1, const float* d_img2,
+                                int nx, int ny, int nc, const octane_params* p,
+                                float* d_u_inout, float* d_v_inout);
+int octane_pix2uv_dev(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
+                      const float* d_u, const float* d_v, int nx, int ny, const octane_params* p,
+                      short* d_U, short* d_V, short* d_U_raw, short* d_V_raw);
+
+/* ---- stage entry points (device pointers; used by the parity tests) ----- */
+int octane_stage_blur_decimate(octane_ctx* ctx, const float* d_img, int nx, int ny, int nc,
+                               float factor, float* d_out /* nxx*nyy*nc dense */);
+int octane_stage_gradient(octane_ctx* ctx, const float* d_f, int xi, int yi, int nc,
+                          float* d_gx, float* d_gy);
+int octane_stage_zoom_in(octane_ctx* ctx, const float* d_flow, int nx, int ny, int nxx, int nyy,
+                         float sf, float* d_out);
+/* coef: 7 dense planes [a1,a2,a4,a5,a6,a7,a8] with the boundary merging applied */
+int octane_stage_build(octane_ctx* ctx, const float* d_u, const float* d_v,
+                       const float* d_uh, const float* d_vh,
+                       const float* d_g1, const float* d_g2, int xi, int yi, int nc,
+                       const octane_params* p, float lambdac_level, int gnc,
+                       float* d_coef, float* d_bu, float* d_bv);
+int octane_stage_pcg(octane_ctx* ctx, const float* d_coef, const float* d_bu, const float* d_bv,
+                     int xi, int yi, int iters, float tol, float* d_xu, float* d_xv, int* iterations);
+
+/* ---- row-band multi-GPU (one process per GPU) --------------------------- */
+/* Rank r of `world` owns finest-level rows [own0,own1) and must supply
+ * full-resolution input rows [in0,in1) (band + blur/gradient/warp overlap). */
+int octane_band_plan(int nx, int ny, const octane_params* p, int rank, int world,
+                     int* own0, int* own1, int* in0, int* in1);
+/* NCCL bootstrap: rank 0 calls octane_comm_unique_id, the host framework
+ * broadcasts the 128 bytes, every rank calls octane_comm_init. */
+int octane_comm_unique_id(char id[128]);
+int octane_comm_init(octane_ctx* ctx, const char id[128], int rank, int world);
+int octane_comm_rank(octane_ctx* ctx, int* rank, int* world);
+/* d_img*: rows [in0,in1) dense; d_u/d_v: rows [own0,own1) dense (in/out). */
+int octane_variational_flow_band_dev(octane_ctx* ctx, const float* d_img1_band, const float* d_img2_band,
+                                     int nx, int ny, int nc, const octane_params* p,
+                                     float* d_u_band_inout, float* d_v_band_inout);
+/* rows [row0,row0+nrows) of an nx-wide scene; d_u etc. hold just those rows */
+int octane_pix2uv_band_dev(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
+                           const float* d_u, const float* d_v, int nx, int row0, int nrows,
+                           const octane_params* p,
+                           short* d_U, short* d_V, short* d_U_raw, short* d_V_raw);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCTANE_B200_H */

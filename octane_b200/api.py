@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference's operator surface for the hot path.
+
+The reference exposes three C++ functions on this path (no library, no Python):
+
+    oct_variational_optical_flow(Image, Image, float* CTH, float* u, float* v, nx, ny, nc, OFFlags)
+        src/oct_variational_optical_flow.cu:1213
+    oct_pix2uv_cuda(GOESVar&, double t2, float* u, float* v, short* ur, short* vr,
+                    short* ur2, short* vr2, OFFlags)              src/oct_pix2uv_cuda.cu:265
+    oct_optical_flow(GOESVar&, GOESVar&, OFFlags&)                src/oct_optical_flow.cc:21
+
+`Context` binds their C-ABI replacements (include/octane_b200.h) with the same
+names, argument meaning (u, v are in/out: first guess in, flow out) and error
+behaviour turned into exceptions.  numpy arrays go through the host-buffer
+entry points (copies inside the call); torch CUDA tensors go through the
+device-pointer entry points on the context's stream.  torch is used only for
+device memory and process-group bootstrap, never for compute.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import Nav, Params, Stats
+
+ERRORS = {-1: "ENODEV", -2: "EINVAL", -3: "ENOMEM", -4: "ECUDA", -5: "EHALO", -6: "ECOMM"}
+
+
+class OctaneError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"octane_b200 {ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def default_params(**kw) -> Params:
+    """OFFlags defaults of src/main.cc:53-108, overridable by flag name
+    (alpha, lambda_, lambdac, kiters, liters, cgiters, dozim, pixuv, ...)."""
+    p = Params()
+    _lib.load().octane_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
+def goes_nav(xScale, yScale, xOffset, yOffset, pph=35786023.0, req=6378137.0, rpol=6356752.31414,
+             lon0_deg=-75.0, minX=0, minY=0, g2xOffset=None, g2yOffset=None) -> Nav:
+    lam0 = lon0_deg * (3.14159265 / 180.0)
+    return Nav(pph, req, rpol, lam0, xScale, xOffset, yScale, yOffset,
+               xOffset if g2xOffset is None else g2xOffset, yOffset if g2yOffset is None else g2yOffset,
+               0.0, 0.0, 0.0, 6371000.0, minX, minY)
+
+
+def level_dims(nx: int, ny: int, p: Optional[Params] = None):
+    p = p or default_params()
+    L = _lib.load()
+    out = []
+    for k in range(p.kiters):
+        a, b = C.c_int(), C.c_int()
+        L.octane_level_dims(nx, ny, C.byref(p), k, C.byref(a), C.byref(b))
+        out.append((a.value, b.value))
+    return out
+
+
+def band_plan(nx: int, ny: int, p: Params, rank: int, world: int):
+    """(own0, own1, in0, in1): finest rows solved by `rank`, full-res input rows it needs."""
+    L = _lib.load()
+    v = [C.c_int() for _ in range(4)]
+    rc = L.octane_band_plan(nx, ny, C.byref(p), rank, world, *[C.byref(x) for x in v])
+    if rc < 0:
+        raise OctaneError(rc, L.octane_last_error().decode())
+    return tuple(x.value for x in v)
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(x.ctypes.data)
+
+
+class Context:
+    """octane_ctx: a CUDA stream plus a reusable device workspace."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        rc = self._L.octane_ctx_create(C.byref(h), device)
+        if rc < 0:
+            raise OctaneError(rc, self._L.octane_last_error().decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.octane_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise OctaneError(rc, self._L.octane_last_error().decode())
+        return rc
+
+    # ---- knobs / stats
+    def set_profile(self, on: bool):
+        self._check(self._L.octane_ctx_set_profile(self._h, int(on)))
+
+    def set_graphs(self, on: bool):
+        self._check(self._L.octane_ctx_set_graphs(self._h, int(on)))
+
+    def synchronize(self):
+        self._check(self._L.octane_ctx_synchronize(self._h))
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self._L.octane_get_stats(self._h, C.byref(s)))
+        return s
+
+    # ---- multi-GPU bootstrap (one process per GPU)
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        self._check(self._L.octane_comm_init(self._h, unique_id, rank, world))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        L = _lib.load()
+        buf = C.create_string_buffer(128)
+        rc = L.octane_comm_unique_id(buf)
+        if rc < 0:
+            raise OctaneError(rc, L.octane_last_error().decode())
+        return buf.raw
+
+    # ---- the reference's operators
+    def oct_variational_optical_flow(self, geo1, geo2, u, v, p: Optional[Params] = None, nc: int = 1):
+        """u, v in/out (ny x nx float32).  numpy -> host entry point; torch CUDA -> device entry point."""
+        p = p or default_params()
+        ny, nx = geo1.shape[-2:]
+        if _is_torch(geo1):
+            fn = self._L.octane_variational_flow_dev
+        else:
+            fn = self._L.octane_variational_flow
+            for a in (geo1, geo2, u, v):
+                assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+        self._check(fn(self._h, _ptr(geo1), _ptr(geo2), nx, ny, nc, C.byref(p), _ptr(u), _ptr(v)))
+        return u, v
+
+    def oct_variational_optical_flow_band(self, geo1_band, geo2_band, u_band, v_band, nx, ny, p: Params, nc: int = 1):
+        self._check(self._L.octane_variational_flow_band_dev(self._h, _ptr(geo1_band), _ptr(geo2_band), nx, ny, nc,
+                                                             C.byref(p), _ptr(u_band), _ptr(v_band)))
+        return u_band, v_band
+
+    def oct_pix2uv_cuda(self, nav: Nav, t1: float, t2: float, u, v, ur, vr, ur2, vr2, p: Optional[Params] = None):
+        """Returns (dT, moved): moved=True when the sector-moved guard zeroed the outputs."""
+        p = p or default_params()
+        ny, nx = u.shape
+        if _is_torch(u):
+            rc = self._check(self._L.octane_pix2uv_dev(self._h, C.byref(nav), t1, t2, _ptr(u), _ptr(v), nx, ny,
+                                                       C.byref(p), _ptr(ur), _ptr(vr), _ptr(ur2), _ptr(vr2)))
+            return float(np.float32(t2 - t1)), rc == 1
+        dT = C.c_float()
+        rc = self._check(self._L.octane_pix2uv(self._h, C.byref(nav), t1, t2, _ptr(u), _ptr(v), nx, ny, C.byref(p),
+                                               _ptr(ur), _ptr(vr), _ptr(ur2), _ptr(vr2), C.byref(dT)))
+        return dT.value, rc == 1
+
+    def oct_pix2uv_band(self, nav: Nav, t1, t2, u, v, nx, row0, nrows, ur, vr, ur2, vr2, p: Params):
+        return self._check(self._L.octane_pix2uv_band_dev(self._h, C.byref(nav), t1, t2, _ptr(u), _ptr(v), nx, row0,
+                                                          nrows, C.byref(p), _ptr(ur), _ptr(vr), _ptr(ur2), _ptr(vr2)))
+
+    def oct_optical_flow(self, geo1, geo2, nav: Nav, t1: float, t2: float, p: Optional[Params] = None,
+                         cth=None, upix=None, vpix=None, nc: int = 1):
+        """Dispatcher (host arrays): returns dict(uPix, vPix, uVal, vVal, uVal2, vVal2, CTP, dT)."""
+        p = p or default_params()
+        ny, nx = geo1.shape[-2:]
+        upix = np.zeros((ny, nx), np.float32) if upix is None else upix
+        vpix = np.zeros((ny, nx), np.float32) if vpix is None else vpix
+        out = {k: np.zeros((ny, nx), np.int16) for k in ("uVal", "vVal", "uVal2", "vVal2")}
+        ctp = np.zeros((ny, nx), np.int16) if p.doCTH else None
+        dT = C.c_float()
+        self._check(self._L.octane_optical_flow(self._h, _ptr(geo1), _ptr(geo2), _ptr(cth), nx, ny, nc, C.byref(nav),
+                                                t1, t2, C.byref(p), _ptr(upix), _ptr(vpix), _ptr(out["uVal"]),
+                                                _ptr(out["vVal"]), _ptr(out["uVal2"]), _ptr(out["vVal2"]),
+                                                _ptr(ctp), C.byref(dT)))
+        out.update(uPix=upix, vPix=vpix, CTP=ctp, dT=dT.value)
+        return out
+
+    # ---- stage entry points (device pointers; parity tests)
+    def stage_blur_decimate(self, d_img, nx, ny, nc, factor, d_out):
+        self._check(self._L.octane_stage_blur_decimate(self._h, _ptr(d_img), nx, ny, nc, factor, _ptr(d_out)))
+
+    def stage_gradient(self, d_f, xi, yi, nc, d_gx, d_gy):
+        self._check(self._L.octane_stage_gradient(self._h, _ptr(d_f), xi, yi, nc, _ptr(d_gx), _ptr(d_gy)))
+
+    def stage_zoom_in(self, d_flow, nx, ny, nxx, nyy, sf, d_out):
+        self._check(self._L.octane_stage_zoom_in(self._h, _ptr(d_flow), nx, ny, nxx, nyy, sf, _ptr(d_out)))
+
+    def stage_build(self, d_u, d_v, d_uh, d_vh, d_g1, d_g2, xi, yi, nc, p, lambdac, gnc, d_coef, d_bu, d_bv):
+        self._check(self._L.octane_stage_build(self._h, _ptr(d_u), _ptr(d_v), _ptr(d_uh), _ptr(d_vh), _ptr(d_g1),
+                                               _ptr(d_g2), xi, yi, nc, C.byref(p), lambdac, gnc, _ptr(d_coef),
+                                               _ptr(d_bu), _ptr(d_bv)))
+
+    def stage_pcg(self, d_coef, d_bu, d_bv, xi, yi, iters, tol, d_xu, d_xv) -> int:
+        its = C.c_int()
+        self._check(self._L.octane_stage_pcg(self._h, _ptr(d_coef), _ptr(d_bu), _ptr(d_bv), xi, yi, iters, tol,
+                                             _ptr(d_xu), _ptr(d_xv), C.byref(its)))
+        return its.value

@@ -1,0 +1,30 @@
+// comm.h -- row-band halo exchange and scalar all-reduce over NCCL (NVLink 5 /
+// NVSwitch).  The reference has no multi-GPU layer at all (SURVEY.md 2,
+// "Parallelism strategies": none), so there is no reference file to cite; the
+// exchange steps are the ones SURVEY.md 8(e) derives from the stencil radii.
+// NCCL is loaded with dlopen so a single-GPU build has no NCCL dependency and a
+// process that already holds torch's bundled libnccl shares that copy.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace octane {
+
+struct Comm {
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+int comm_unique_id(char id[128]);
+int comm_init(Comm* c, const char id[128], int rank, int world);
+void comm_destroy(Comm* c);
+// in-place sum of n doubles on the stream
+int comm_allreduce_f64(Comm* c, double* d_buf, int n, cudaStream_t st);
+// One exchange step for several planes at once: for each plane p, send `count`
+// floats starting at send_up[p] to rank-1 and send_dn[p] to rank+1, receive the
+// neighbours' counterparts into recv_up[p] (from rank-1) and recv_dn[p] (from rank+1).
+int comm_halo_exchange(Comm* c, int nplanes, float* const* send_up, float* const* recv_up,
+                       float* const* send_dn, float* const* recv_dn, size_t count, cudaStream_t st);
+const char* comm_last_error();
+
+}  // namespace octane

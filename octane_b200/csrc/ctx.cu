@@ -1,0 +1,1097 @@
+// ctx.cu -- context, workspace, coarse-to-fine driver and the C ABI of
+// include/octane_b200.h.
+//
+// Host-side counterpart of the reference's wrapper
+// oct_variational_optical_flow (src/oct_variational_optical_flow.cu:1213-1473)
+// and of the level / GNC / inner-iteration control flow that the reference
+// runs inside its single cooperative kernel (:487-1210).  Here the control
+// flow lives on the host as a stream of kernel launches (the PCG loop replayed
+// from a CUDA graph), with every data-dependent decision (stop rule, alpha,
+// beta) taken on the device, so the host never synchronises inside a solve.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/octane_b200.h"
+#include "comm.h"
+#include "kernels.cuh"
+
+using namespace octane;
+
+namespace {
+
+thread_local char g_err[512] = "";
+void set_err(const char* fmt, const char* a = "", const char* b = "")
+{
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+}
+
+#define CUDA_OK(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            set_err("%s: %s", #call, cudaGetErrorString(e_));                          \
+            return (e_ == cudaErrorMemoryAllocation) ? OCTANE_ENOMEM : OCTANE_ECUDA;   \
+        }                                                                              \
+    } while (0)
+
+// ---- pyramid geometry (:50-54, :488, :521-526) -------------------------------------
+float level_factor(const octane_params& p, int k)
+{
+    float sf = (float)p.scaleF;
+    return (float)pow((double)sf, (double)(p.kiters - k - 1));
+}
+void zoom_size(int nx, int ny, float factor, int* nxx, int* nyy)
+{
+    double f = (double)factor;
+    *nxx = (int)((double)nx * f + 0.5);
+    *nyy = (int)((double)ny * f + 0.5);
+}
+int filter_radius(float factor)
+{
+    float sigma = (float)(1.0 / sqrt(2. * (double)factor));
+    int filtsize = (int)(2 * sigma);
+    if (filtsize < 5) filtsize = 5;
+    return filtsize;
+}
+
+constexpr int HALO_UV = 4;   // rows of u,v kept valid beyond the owned band (3x3 build + bicubic prolongation)
+
+struct Level {
+    float factor;
+    int R;
+    int own0, own1;          // rows this rank solves
+    Geom g;                  // local storage
+    float lambdac;
+};
+
+struct Plan {
+    int nx = 0, ny = 0, nc = 0, rank = 0, world = 1;
+    octane_params p;
+    std::vector<Level> lv;
+    int in0 = 0, in1 = 0;    // full-res input rows needed (== finest level's local rows)
+    size_t P = 0, Pc = 0;    // plane sizes (floats): finest, second finest
+    bool same(int nx_, int ny_, int nc_, const octane_params& q, int rank_, int world_) const
+    {
+        return nx == nx_ && ny == ny_ && nc == nc_ && rank == rank_ && world == world_ &&
+               memcmp(&p, &q, sizeof q) == 0;
+    }
+};
+
+int make_plan(Plan& pl, int nx, int ny, int nc, const octane_params& p, int rank, int world)
+{
+    if (nx < 4 || ny < 4 || nc < 1 || nc > 3 || p.kiters < 1 || p.kiters > 16 || p.liters < 0 ||
+        p.cgiters < 0 || !(p.scaleF > 0.0 && p.scaleF < 1.0) || !(p.alpha > 0.0) ||
+        p.kiters * 3 * p.liters > OCTANE_MAX_SOLVES) {
+        set_err("invalid size or parameters");
+        return OCTANE_EINVAL;
+    }
+    pl.nx = nx; pl.ny = ny; pl.nc = nc; pl.rank = rank; pl.world = world; pl.p = p;
+    const int K = p.kiters;
+    pl.lv.assign(K, Level());
+    const float lambdaco = (float)(p.lambdac / p.alpha);      // :1236
+    int in0 = ny, in1 = 0;
+    for (int k = 0; k < K; k++) {
+        Level& L = pl.lv[k];
+        L.factor = level_factor(p, k);
+        L.R = filter_radius(L.factor);
+        int xi, yi;
+        zoom_size(nx, ny, L.factor, &xi, &yi);
+        if (xi < 4 || yi < 4) { set_err("pyramid level smaller than 4 pixels"); return OCTANE_EINVAL; }
+        L.lambdac = (float)((double)lambdaco * pow(0.5, k));  // :494
+        L.own0 = (int)((long long)rank * yi / world);
+        L.own1 = (int)((long long)(rank + 1) * yi / world);
+        int lo = 0, hi = yi;
+        if (world > 1) {
+            // image-2 fields are gathered at (j + v): warp halo, +4 rows so the second
+            // derivatives there are valid, never less than the u,v halo
+            int W = (int)ceil((double)p.max_disp * L.factor) + 3;
+            int H = W + 4;
+            if (H < HALO_UV) H = HALO_UV;
+            lo = L.own0 - H; if (lo < 0) lo = 0;
+            hi = L.own1 + H; if (hi > yi) hi = yi;
+            if (L.own1 - L.own0 < 2 * HALO_UV) { set_err("band thinner than the halo: fewer ranks or larger scene"); return OCTANE_EINVAL; }
+        }
+        L.g.nx = xi; L.g.ny = yi; L.g.pitch = round_up(xi, 32); L.g.j0 = lo; L.g.rows = hi - lo;
+        // full-res rows this level's blur reads (:369-370: j2 = (int)(jj/factor))
+        if (k < K - 1) {
+            int a = (int)(lo / L.factor) - L.R, b = (int)((hi - 1) / L.factor) + L.R;
+            if (a < in0) in0 = a;
+            if (b > in1) in1 = b;
+        } else {
+            if (lo < in0) in0 = lo;
+            if (hi > in1) in1 = hi;
+        }
+    }
+    if (in0 < 0) in0 = 0;
+    if (in1 > ny) in1 = ny;
+    Level& F = pl.lv[K - 1];
+    F.g.j0 = in0; F.g.rows = in1 - in0;          // the finest level IS the input band
+    pl.in0 = in0; pl.in1 = in1;
+    for (int k = 0; k < K; k++) pl.lv[k].g.plane = (long long)pl.lv[k].g.rows * pl.lv[k].g.pitch;
+    pl.P = (size_t)F.g.plane;
+    pl.Pc = (K > 1) ? (size_t)pl.lv[K - 2].g.plane : 0;
+    for (int k = 0; k + 1 < K; k++)
+        if ((size_t)pl.lv[k].g.plane > pl.Pc) pl.Pc = (size_t)pl.lv[k].g.plane;
+    return OCTANE_OK;
+}
+
+struct Buffers {
+    float *img1, *img2, *g1c, *g2c;
+    float *g1x, *g1y, *g2x, *g2y, *g2xx, *g2xy, *g2yy;
+    float *u, *v, *ut, *vt;
+    float *uh, *vh, *hu, *hv;
+    PcgBuffers pcg;
+};
+
+struct TimedEvent { cudaEvent_t a, b; int cat, level, solve, ki; };
+enum { CAT_PYR = 0, CAT_BUILD, CAT_P1, CAT_P2, CAT_UPDATE, CAT_NAV, CAT_TOTAL, CAT_N };
+
+}  // namespace
+
+struct octane_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool profile = false, graphs = true;
+    Comm comm;
+    // workspace
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    Plan plan;
+    bool plan_valid = false;
+    Buffers buf;
+    std::vector<cudaGraphExec_t> pcg_graph;   // one per level
+    // small persistent device objects
+    PcgScalars* d_scal = nullptr;
+    double* d_pending = nullptr;
+    unsigned* d_ticket = nullptr;
+    double* d_partials = nullptr;
+    int partial_blocks = 0;
+    int* d_its = nullptr;
+    int* h_its = nullptr;          // pinned
+    PcgScalars* h_scal = nullptr;  // pinned
+    float* d_gk = nullptr;
+    // host-API staging (device)
+    char* stage = nullptr;
+    size_t stage_bytes = 0;
+    octane_stats stats;
+    long long launches = 0;
+    std::vector<TimedEvent> events;
+    std::vector<cudaEvent_t> event_pool;
+    size_t event_next = 0;
+};
+
+namespace {
+
+void destroy_graphs(octane_ctx* c)
+{
+    for (auto g : c->pcg_graph) if (g) cudaGraphExecDestroy(g);
+    c->pcg_graph.clear();
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t arena_layout(const Plan& pl, Buffers* b, char* base)
+{
+    size_t off = 0;
+    auto take = [&](size_t nfloats) -> float* {
+        float* p = base ? (float*)(base + off) : nullptr;
+        off += align_up(nfloats * sizeof(float));
+        return p;
+    };
+    const size_t P = pl.P, Pc = pl.Pc, nc = pl.nc;
+    Buffers tmp;
+    Buffers& B = b ? *b : tmp;
+    B.img1 = take(P * nc); B.img2 = take(P * nc);
+    B.g1c = take(Pc * nc); B.g2c = take(Pc * nc);
+    B.g1x = take(P * nc); B.g1y = take(P * nc); B.g2x = take(P * nc); B.g2y = take(P * nc);
+    B.g2xx = take(P * nc); B.g2xy = take(P * nc); B.g2yy = take(P * nc);
+    B.u = take(P); B.v = take(P); B.ut = take(Pc); B.vt = take(Pc);
+    if (pl.p.first_guess) { B.uh = take(P); B.vh = take(P); B.hu = take(Pc); B.hv = take(Pc); }
+    else { B.uh = B.vh = B.hu = B.hv = nullptr; }
+    for (int i = 0; i < 7; i++) B.pcg.coef[i] = take(P);
+    B.pcg.ru = take(P); B.pcg.rv = take(P); B.pcg.xu = take(P); B.pcg.xv = take(P);
+    B.pcg.pu[0] = take(P); B.pcg.pu[1] = take(P); B.pcg.pv[0] = take(P); B.pcg.pv[1] = take(P);
+    B.pcg.qu = take(P); B.pcg.qv = take(P);
+    return off;
+}
+
+int ensure_small(octane_ctx* c, int partial_blocks)
+{
+    if (!c->d_scal) {
+        CUDA_OK(cudaMalloc(&c->d_scal, sizeof(PcgScalars)));
+        CUDA_OK(cudaMemset(c->d_scal, 0, sizeof(PcgScalars)));
+        CUDA_OK(cudaMalloc(&c->d_pending, 2 * sizeof(double)));
+        CUDA_OK(cudaMemset(c->d_pending, 0, 2 * sizeof(double)));
+        CUDA_OK(cudaMalloc(&c->d_ticket, sizeof(unsigned)));
+        CUDA_OK(cudaMemset(c->d_ticket, 0, sizeof(unsigned)));
+        CUDA_OK(cudaMalloc(&c->d_its, OCTANE_MAX_SOLVES * sizeof(int)));
+        CUDA_OK(cudaMemset(c->d_its, 0, OCTANE_MAX_SOLVES * sizeof(int)));
+        CUDA_OK(cudaMallocHost(&c->h_its, OCTANE_MAX_SOLVES * sizeof(int)));
+        CUDA_OK(cudaMallocHost(&c->h_scal, sizeof(PcgScalars)));
+        memset(c->h_scal, 0, sizeof(PcgScalars));
+        CUDA_OK(cudaMalloc(&c->d_gk, 256 * sizeof(float)));
+    }
+    if (partial_blocks > c->partial_blocks) {
+        if (c->d_partials) cudaFree(c->d_partials);
+        c->d_partials = nullptr;
+        CUDA_OK(cudaMalloc(&c->d_partials, (size_t)partial_blocks * 2 * sizeof(double)));
+        c->partial_blocks = partial_blocks;
+    }
+    return OCTANE_OK;
+}
+
+// (re)build plan + workspace for this problem; cached across calls
+int prepare(octane_ctx* c, int nx, int ny, int nc, const octane_params& p)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->plan_valid && c->plan.same(nx, ny, nc, p, c->comm.rank, c->comm.world)) return OCTANE_OK;
+    c->plan_valid = false;
+    destroy_graphs(c);
+    Plan pl;
+    int rc = make_plan(pl, nx, ny, nc, p, c->comm.rank, c->comm.world);
+    if (rc) return rc;
+    const size_t need = arena_layout(pl, nullptr, nullptr);
+    if (need > c->arena_bytes) {
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (c->arena) cudaFree(c->arena);
+        c->arena = nullptr; c->arena_bytes = 0;
+        CUDA_OK(cudaMalloc(&c->arena, need));
+        c->arena_bytes = need;
+    }
+    // padding columns / halo rows must hold finite values (they are multiplied by zero
+    // coefficients): clear the whole workspace once per plan
+    CUDA_OK(cudaMemsetAsync(c->arena, 0, need, c->stream));
+    arena_layout(pl, &c->buf, c->arena);
+    int pb = c->sm_count * 16;
+    const Level& F = pl.lv.back();
+    int bb = build_partial_blocks(F.g, F.g.rows);
+    for (auto& L : pl.lv) { int t = build_partial_blocks(L.g, L.g.rows); if (t > bb) bb = t; }
+    if (bb > pb) pb = bb;
+    rc = ensure_small(c, pb);
+    if (rc) return rc;
+    c->buf.pcg.scal = c->d_scal;
+    c->buf.pcg.partials = c->d_partials;
+    c->buf.pcg.ticket = c->d_ticket;
+    c->buf.pcg.max_partial_blocks = c->partial_blocks;
+    c->buf.pcg.pending = c->d_pending;
+    c->buf.pcg.defer = (c->comm.world > 1) ? 1 : 0;
+    c->plan = pl;
+    c->pcg_graph.assign(pl.lv.size(), nullptr);
+    c->plan_valid = true;
+    return OCTANE_OK;
+}
+
+// ---- profile-mode event helpers ------------------------------------------------------
+cudaEvent_t next_event(octane_ctx* c)
+{
+    if (c->event_next == c->event_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->event_pool.push_back(e);
+    }
+    return c->event_pool[c->event_next++];
+}
+struct Scope {
+    octane_ctx* c; TimedEvent ev; bool on;
+    Scope(octane_ctx* c_, int cat, int level = -1, int solve = -1, int ki = -1) : c(c_), on(c_->profile)
+    {
+        if (!on) return;
+        ev.cat = cat; ev.level = level; ev.solve = solve; ev.ki = ki;
+        ev.a = next_event(c); ev.b = next_event(c);
+        cudaEventRecord(ev.a, c->stream);
+    }
+    ~Scope()
+    {
+        if (!on) return;
+        cudaEventRecord(ev.b, c->stream);
+        c->events.push_back(ev);
+    }
+};
+
+// ---- halo exchange of whole rows (banded runs) ------------------------------------------
+int exchange_rows(octane_ctx* c, const Level& L, int nplanes, float* const* planes, int h)
+{
+    if (c->comm.world <= 1) return OCTANE_OK;
+    const Geom& g = L.g;
+    // interior cuts always have h rows of halo on both sides (make_plan); the outermost
+    // ranks have no neighbour there and comm_halo_exchange skips those pointers
+    float *su[8], *ru[8], *sd[8], *rd[8];
+    const bool has_up = c->comm.rank > 0, has_dn = c->comm.rank + 1 < c->comm.world;
+    for (int p = 0; p < nplanes; p++) {
+        su[p] = planes[p] + g.at(0, L.own0);                          // my first owned rows -> rank-1's lower halo
+        ru[p] = has_up ? planes[p] + g.at(0, L.own0 - h) : nullptr;   // rank-1's last owned rows -> my upper halo
+        sd[p] = planes[p] + g.at(0, L.own1 - h);                      // my last owned rows -> rank+1's upper halo
+        rd[p] = has_dn ? planes[p] + g.at(0, L.own1) : nullptr;       // rank+1's first owned rows -> my lower halo
+    }
+    if (comm_halo_exchange(&c->comm, nplanes, su, ru, sd, rd, (size_t)h * g.pitch, c->stream)) {
+        set_err("%s", comm_last_error());
+        return OCTANE_ECOMM;
+    }
+    return OCTANE_OK;
+}
+
+int allreduce_pending(octane_ctx* c, int n)
+{
+    if (c->comm.world <= 1) return OCTANE_OK;
+    if (comm_allreduce_f64(&c->comm, c->d_pending, n, c->stream)) { set_err("%s", comm_last_error()); return OCTANE_ECOMM; }
+    return OCTANE_OK;
+}
+
+// ---- the PCG loop of one solve (:1129-1182), enqueued or captured ----------------------
+int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve)
+{
+    const PcgBuffers& b = c->buf.pcg;
+    const int iters = c->plan.p.cgiters;
+    const bool multi = c->comm.world > 1;
+    int cur = 0;
+    for (int ki = 0; ki < iters; ki++) {
+        {
+            Scope s(c, CAT_P1, level, solve, ki);
+            launch_pcg_pass1(b, L.g, L.own0, L.own1, ki == 0, cur, multi, c->sm_count, c->stream);
+            c->launches++;
+        }
+        if (multi) {
+            int rc = allreduce_pending(c, 1); if (rc) return rc;
+            launch_finalize(b, FINALIZE_PASS1, 0.f, c->stream); c->launches++;
+        }
+        {
+            Scope s(c, CAT_P2, level, solve, ki);
+            launch_pcg_pass2(b, L.g, L.own0, L.own1, ki == 0, cur, c->sm_count, c->stream);
+            c->launches++;
+        }
+        if (multi) {
+            int rc = allreduce_pending(c, 2); if (rc) return rc;
+            launch_finalize(b, FINALIZE_PASS2, 0.f, c->stream); c->launches++;
+            float* planes[2] = { b.ru, b.rv };            // next pass 1 rebuilds p on the halo rows from r
+            rc = exchange_rows(c, L, 2, planes, 1); if (rc) return rc;
+        }
+        cur ^= 1;
+    }
+    return OCTANE_OK;
+}
+
+int run_pcg(octane_ctx* c, const Level& L, int level, int solve)
+{
+    if (c->plan.p.cgiters <= 0) return OCTANE_OK;
+    if (!c->graphs || c->profile) return enqueue_pcg(c, L, level, solve);
+    if (!c->pcg_graph[level]) {
+        cudaGraph_t graph = nullptr;
+        const long long before = c->launches;
+        CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_pcg(c, L, level, solve);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        c->launches = before;
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) { set_err("cudaStreamEndCapture: %s", cudaGetErrorString(e)); return OCTANE_ECUDA; }
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { set_err("cudaGraphInstantiate: %s", cudaGetErrorString(e)); return OCTANE_ECUDA; }
+        c->pcg_graph[level] = exec;
+    }
+    CUDA_OK(cudaGraphLaunch(c->pcg_graph[level], c->stream));
+    c->launches += (long long)c->plan.p.cgiters * (c->comm.world > 1 ? 4 : 2);
+    return OCTANE_OK;
+}
+
+// ---- coarse-to-fine driver (:487-1210) ----------------------------------------------------
+// Inputs are already in buf.img1/img2 (pitched, rows [in0,in1)) and, with a first guess,
+// buf.uh/vh.  Output: buf.u/v at the finest level.
+int run_levels(octane_ctx* c)
+{
+    Plan& pl = c->plan;
+    Buffers& B = c->buf;
+    const octane_params& p = pl.p;
+    const int K = p.kiters, nc = pl.nc;
+    cudaStream_t st = c->stream;
+    const bool multi = c->comm.world > 1;
+    const float sf = (float)p.scaleF;
+    int solve = 0;
+    for (int k = 0; k < K; k++) {
+        const Level& L = pl.lv[k];
+        const Geom& g = L.g;
+        const bool finest = (k == K - 1);
+        float *g1 = finest ? B.img1 : B.g1c, *g2 = finest ? B.img2 : B.g2c;
+        const float *hu = nullptr, *hv = nullptr;
+        {
+            Scope s(c, CAT_PYR, k);
+            if (k > 0) {                                          // :498-503
+                const Level& Lc = pl.lv[k - 1];
+                launch_zoom_in(B.ut, Lc.g, B.u, g, L.own0, L.own1, sf, st);
+                launch_zoom_in(B.vt, Lc.g, B.v, g, L.own0, L.own1, sf, st);
+                c->launches += 2;
+                float* planes[2] = { B.u, B.v };
+                int rc = exchange_rows(c, L, 2, planes, HALO_UV); if (rc) return rc;
+            }
+            if (!finest) {                                        // :518-564
+                const Geom& gF = pl.lv[K - 1].g;
+                launch_fill_gk(c->d_gk, L.factor, L.R, st);
+                launch_blur_decimate(B.img1, gF, B.g1c, g, g.jlo(), g.jhi(), L.factor, c->d_gk, L.R, 1.f, nc, st);
+                launch_blur_decimate(B.img2, gF, B.g2c, g, g.jlo(), g.jhi(), L.factor, c->d_gk, L.R, 1.f, nc, st);
+                c->launches += 3;
+                if (p.first_guess) {
+                    launch_blur_decimate(B.uh, gF, B.hu, g, g.jlo(), g.jhi(), L.factor, c->d_gk, L.R, L.factor, 1, st);
+                    launch_blur_decimate(B.vh, gF, B.hv, g, g.jlo(), g.jhi(), L.factor, c->d_gk, L.R, L.factor, 1, st);
+                    c->launches += 2;
+                    hu = B.hu; hv = B.hv;
+                }
+            } else if (p.first_guess) {                           // :504-517
+                hu = B.uh; hv = B.vh;
+            }
+            if (k == 0) {                                         // :576-585
+                if (hu) {
+                    CUDA_OK(cudaMemcpyAsync(B.u, hu, (size_t)g.plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                    CUDA_OK(cudaMemcpyAsync(B.v, hv, (size_t)g.plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                } else {
+                    CUDA_OK(cudaMemsetAsync(B.u, 0, (size_t)g.plane * sizeof(float), st));
+                    CUDA_OK(cudaMemsetAsync(B.v, 0, (size_t)g.plane * sizeof(float), st));
+                }
+            }
+            // :587-595 (the third call's y-output is overwritten by the fourth, as in the reference)
+            launch_gradient(g1, B.g1x, B.g1y, g, g.jlo(), g.jhi(), nc, st);
+            launch_gradient(g2, B.g2x, B.g2y, g, g.jlo(), g.jhi(), nc, st);
+            launch_gradient(B.g2x, B.g2xx, B.g2xy, g, g.jlo(), g.jhi(), nc, st);
+            launch_gradient(B.g2y, B.g2xy, B.g2yy, g, g.jlo(), g.jhi(), nc, st);
+            c->launches += 4;
+        }
+        LevelFields f;
+        f.g1 = g1; f.g1x = B.g1x; f.g1y = B.g1y;
+        f.g2 = g2; f.g2x = B.g2x; f.g2y = B.g2y; f.g2xx = B.g2xx; f.g2xy = B.g2xy; f.g2yy = B.g2yy;
+        f.u = B.u; f.v = B.v;
+        f.uh = (L.lambdac != 0.f) ? hu : nullptr;
+        f.vh = (L.lambdac != 0.f) ? hv : nullptr;
+        BuildParams bp;
+        bp.alpha = p.alpha; bp.lambdadalpha = p.lambda / p.alpha; bp.lambdac = L.lambdac;
+        bp.dozim = p.dozim != 0; bp.nchan = nc; bp.tol = 0.0001 * 0.0001;       // :1353
+        // rows to build: owned rows plus one halo row each side (pass 1 rebuilds p there)
+        int ba = L.own0, bb = L.own1;
+        if (multi) { if (ba > 0) ba--; if (bb < g.ny) bb++; }
+        for (int gnc = 0; gnc < 3; gnc++) {                       // :604-608
+            bp.al1 = 1. - 0.5 * gnc;
+            for (int l = 0; l < p.liters; l++, solve++) {
+                {
+                    Scope s(c, CAT_BUILD, k, solve);
+                    launch_build(f, B.pcg, g, ba, bb, L.own0, L.own1, bp, multi ? 1 : 0, st);
+                    c->launches += 2;
+                    if (multi) {
+                        int rc = allreduce_pending(c, 2); if (rc) return rc;
+                        launch_finalize(B.pcg, FINALIZE_BUILD, bp.tol, st); c->launches++;
+                    }
+                }
+                int rc = run_pcg(c, L, k, solve);
+                if (rc) return rc;
+                {
+                    Scope s(c, CAT_UPDATE, k, solve);             // :1185-1195
+                    launch_update_uv(B.u, B.v, B.pcg.xu, B.pcg.xv, g, L.own0, L.own1, c->d_scal,
+                                     c->d_its + solve, c->sm_count, st);
+                    c->launches++;
+                    float* planes[2] = { B.u, B.v };
+                    rc = exchange_rows(c, L, 2, planes, HALO_UV); if (rc) return rc;
+                }
+            }
+        }
+        if (!finest) {                                            // :1201-1205
+            CUDA_OK(cudaMemcpyAsync(B.ut, B.u, (size_t)g.plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            CUDA_OK(cudaMemcpyAsync(B.vt, B.v, (size_t)g.plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    CUDA_OK(cudaMemcpyAsync(c->h_its, c->d_its, sizeof(int) * solve, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaGetLastError());
+    return OCTANE_OK;
+}
+
+// dense band rows [in0,in1) -> pitched finest-level planes
+int ingest(octane_ctx* c, const float* d_img1, const float* d_img2, const float* d_u, const float* d_v)
+{
+    const Plan& pl = c->plan;
+    const Geom& g = pl.lv.back().g;
+    const size_t w = (size_t)g.nx * sizeof(float), dp = (size_t)g.pitch * sizeof(float);
+    for (int ch = 0; ch < pl.nc; ch++) {
+        CUDA_OK(cudaMemcpy2DAsync(c->buf.img1 + (size_t)ch * g.plane, dp, d_img1 + (size_t)ch * g.rows * g.nx, w, w,
+                                  g.rows, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_OK(cudaMemcpy2DAsync(c->buf.img2 + (size_t)ch * g.plane, dp, d_img2 + (size_t)ch * g.rows * g.nx, w, w,
+                                  g.rows, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (pl.p.first_guess) {
+        CUDA_OK(cudaMemcpy2DAsync(c->buf.uh, dp, d_u, w, w, g.rows, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_OK(cudaMemcpy2DAsync(c->buf.vh, dp, d_v, w, w, g.rows, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return OCTANE_OK;
+}
+
+int emit(octane_ctx* c, float* d_u, float* d_v)
+{
+    const Level& L = c->plan.lv.back();
+    const Geom& g = L.g;
+    const size_t w = (size_t)g.nx * sizeof(float), dp = (size_t)g.pitch * sizeof(float);
+    CUDA_OK(cudaMemcpy2DAsync(d_u, w, c->buf.u + g.at(0, L.own0), dp, w, L.own1 - L.own0, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(cudaMemcpy2DAsync(d_v, w, c->buf.v + g.at(0, L.own0), dp, w, L.own1 - L.own0, cudaMemcpyDeviceToDevice, c->stream));
+    return OCTANE_OK;
+}
+
+void begin_call(octane_ctx* c)
+{
+    c->launches = 0;
+    c->events.clear();
+    c->event_next = 0;
+}
+
+int solve_dev(octane_ctx* c, const float* d_img1, const float* d_img2, int nx, int ny, int nc,
+              const octane_params* p, float* d_u, float* d_v)
+{
+    if (!c || !d_img1 || !d_img2 || !p || !d_u || !d_v) { set_err("null argument"); return OCTANE_EINVAL; }
+    if (c->comm.world > 1 && p->first_guess) { set_err("first guess is not supported in banded runs yet"); return OCTANE_EINVAL; }
+    int rc = prepare(c, nx, ny, nc, *p);
+    if (rc) return rc;
+    Scope total(c, CAT_TOTAL);
+    rc = ingest(c, d_img1, d_img2, d_u, d_v);
+    if (rc) return rc;
+    rc = run_levels(c);
+    if (rc) return rc;
+    return emit(c, d_u, d_v);
+}
+
+int ensure_stage(octane_ctx* c, size_t bytes)
+{
+    if (bytes <= c->stage_bytes) return OCTANE_OK;
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (c->stage) cudaFree(c->stage);
+    c->stage = nullptr; c->stage_bytes = 0;
+    CUDA_OK(cudaMalloc(&c->stage, bytes));
+    c->stage_bytes = bytes;
+    return OCTANE_OK;
+}
+
+void fill_nav(NavParams& np, const octane_nav* nav, double t1, double t2, const octane_params* p)
+{
+    np.pph = nav->pph; np.req = nav->req; np.rpol = nav->rpol; np.lam0 = nav->lam0;
+    np.xScale = nav->xScale; np.xOffset = nav->xOffset; np.yScale = nav->yScale; np.yOffset = nav->yOffset;
+    np.lat1 = nav->lat1; np.lon1 = nav->lon1; np.lon0 = nav->lon0; np.R = nav->R;
+    np.minX = nav->minX; np.minY = nav->minY; np.t1 = t1; np.t2 = t2;
+    np.pixuv = p->pixuv; np.dp = p->dopolar == 1; np.dm = p->domerc == 1;
+}
+
+// sector-moved guard, src/oct_pix2uv_cuda.cu:295
+bool sector_moved(const octane_nav* nav)
+{
+    float dx = nav->xOffset - nav->g2xOffset, dy = nav->yOffset - nav->g2yOffset;
+    return !(((dx * dx) < (0.00001 * 0.00001)) && ((dy * dy) < (0.00001 * 0.00001)));
+}
+
+int pix2uv_dev_rows(octane_ctx* c, const octane_nav* nav, double t1, double t2, const float* d_u, const float* d_v,
+                    int nx, int row0, int nrows, const octane_params* p, short* U, short* V, short* Ur, short* Vr)
+{
+    if (!c || !nav || !d_u || !d_v || !p || !U || !V || !Ur || !Vr || nx <= 0 || nrows < 0) {
+        set_err("null or invalid argument");
+        return OCTANE_EINVAL;
+    }
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t n = (size_t)nx * nrows;
+    if (sector_moved(nav)) {       // :358-368: all four planes zero
+        CUDA_OK(cudaMemsetAsync(U, 0, n * sizeof(short), c->stream));
+        CUDA_OK(cudaMemsetAsync(V, 0, n * sizeof(short), c->stream));
+        CUDA_OK(cudaMemsetAsync(Ur, 0, n * sizeof(short), c->stream));
+        CUDA_OK(cudaMemsetAsync(Vr, 0, n * sizeof(short), c->stream));
+        return 1;
+    }
+    NavParams np;
+    fill_nav(np, nav, t1, t2, p);
+    {
+        Scope s(c, CAT_NAV);
+        launch_pix2uv(np, d_u, d_v, nx, row0, nrows, U, V, Ur, Vr, c->stream);
+        c->launches++;
+    }
+    CUDA_OK(cudaGetLastError());
+    return OCTANE_OK;
+}
+
+void collect_stats(octane_ctx* c)
+{
+    octane_stats& s = c->stats;
+    const Plan& pl = c->plan;
+    memset(&s, 0, sizeof s);
+    if (!c->plan_valid) return;
+    s.n_levels = (int)pl.lv.size();
+    s.n_solves = pl.p.kiters * 3 * pl.p.liters;
+    double bytes = 0.0;
+    int solve = 0;
+    for (int k = 0; k < s.n_levels; k++) {
+        const Level& L = pl.lv[k];
+        s.level_nx[k] = L.g.nx; s.level_ny[k] = L.g.ny;
+        const double Nk = (double)L.g.nx * (L.own1 - L.own0);
+        bytes += Nk * (100.0 + 3.0 * pl.p.liters * 80.0);
+        for (int q = 0; q < 3 * pl.p.liters; q++, solve++) {
+            s.cg_iterations[solve] = c->h_its[solve];
+            bytes += 124.0 * Nk * c->h_its[solve];
+        }
+    }
+    s.algorithmic_bytes = bytes;
+    s.kernel_launches = c->launches;
+    const Level& F = pl.lv.back();
+    s.finest_pixels = (long long)F.g.nx * (F.own1 - F.own0);
+    double f1 = 0, f2 = 0; long long n1 = 0, n2 = 0;
+    for (auto& e : c->events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess) continue;
+        switch (e.cat) {
+            case CAT_PYR: s.ms_pyramid += ms; break;
+            case CAT_BUILD: s.ms_build += ms; break;
+            case CAT_UPDATE: s.ms_update += ms; break;
+            case CAT_NAV: s.ms_nav += ms; break;
+            case CAT_TOTAL: s.ms_total += ms; break;
+            case CAT_P1:
+            case CAT_P2: {
+                const bool worked = e.solve >= 0 && e.ki < c->h_its[e.solve];
+                if (e.cat == CAT_P1) { s.ms_pcg_pass1 += ms; if (worked) s.n_pcg_pass1++; }
+                else { s.ms_pcg_pass2 += ms; if (worked) s.n_pcg_pass2++; }
+                if (worked && e.level == s.n_levels - 1) {
+                    if (e.cat == CAT_P1) { f1 += ms; n1++; } else { f2 += ms; n2++; }
+                }
+            } break;
+        }
+    }
+    s.finest_pass1_ms = n1 ? f1 / n1 : 0.0;
+    s.finest_pass2_ms = n2 ? f2 / n2 : 0.0;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+int octane_abi_version(void) { return OCTANE_ABI_VERSION; }
+const char* octane_last_error(void) { return g_err; }
+
+int octane_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void octane_params_default(octane_params* p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->alpha = 5.; p->lambda = 1.; p->lambdac = 0.; p->scaleF = 0.5; p->scsig = 400.;   // src/main.cc:77-87
+    p->kiters = 4; p->liters = 3; p->cgiters = 30; p->dozim = 1; p->setdevice = 0;
+    p->pixuv = 0; p->dopolar = 0; p->domerc = 0; p->first_guess = 0; p->max_disp = 64;
+    p->doCTH = 0; p->ir = 0;
+}
+
+int octane_ctx_create(octane_ctx** out, int device)
+{
+    if (!out) { set_err("null argument"); return OCTANE_EINVAL; }
+    *out = nullptr;
+    int n = octane_device_count();
+    if (n == 0) { set_err("no CUDA device: octane_b200 has no CPU fallback"); return OCTANE_ENODEV; }
+    if (device < 0 || device >= n) device = 0;    // reference: warning + device 0, :1260-1264
+    CUDA_OK(cudaSetDevice(device));
+    octane_ctx* c = new octane_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_err("cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return OCTANE_ECUDA; }
+    memset(&c->stats, 0, sizeof c->stats);
+    *out = c;
+    return OCTANE_OK;
+}
+
+void octane_ctx_destroy(octane_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    destroy_graphs(c);
+    comm_destroy(&c->comm);
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->arena) cudaFree(c->arena);
+    if (c->stage) cudaFree(c->stage);
+    if (c->d_scal) cudaFree(c->d_scal);
+    if (c->d_pending) cudaFree(c->d_pending);
+    if (c->d_ticket) cudaFree(c->d_ticket);
+    if (c->d_partials) cudaFree(c->d_partials);
+    if (c->d_its) cudaFree(c->d_its);
+    if (c->d_gk) cudaFree(c->d_gk);
+    if (c->h_its) cudaFreeHost(c->h_its);
+    if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int octane_ctx_set_profile(octane_ctx* c, int on) { if (!c) return OCTANE_EINVAL; c->profile = on != 0; return OCTANE_OK; }
+int octane_ctx_set_graphs(octane_ctx* c, int on) { if (!c) return OCTANE_EINVAL; c->graphs = on != 0; return OCTANE_OK; }
+
+int octane_ctx_synchronize(octane_ctx* c)
+{
+    if (!c) return OCTANE_EINVAL;
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return OCTANE_OK;
+}
+
+int octane_get_stats(octane_ctx* c, octane_stats* out)
+{
+    if (!c || !out) return OCTANE_EINVAL;
+    int rc = octane_ctx_synchronize(c);
+    if (rc) return rc;
+    collect_stats(c);
+    *out = c->stats;
+    return OCTANE_OK;
+}
+
+size_t octane_workspace_bytes(int nx, int ny, int nc, const octane_params* p)
+{
+    if (!p) return 0;
+    Plan pl;
+    if (make_plan(pl, nx, ny, nc, *p, 0, 1)) return 0;
+    return arena_layout(pl, nullptr, nullptr);
+}
+
+int octane_level_dims(int nx, int ny, const octane_params* p, int k, int* xi, int* yi)
+{
+    if (!p || !xi || !yi || k < 0 || k >= p->kiters) return OCTANE_EINVAL;
+    zoom_size(nx, ny, level_factor(*p, k), xi, yi);
+    return OCTANE_OK;
+}
+
+int octane_variational_flow_dev(octane_ctx* c, const float* d_img1, const float* d_img2, int nx, int ny, int nc,
+                                const octane_params* p, float* d_u, float* d_v)
+{
+    if (!c) return OCTANE_EINVAL;
+    if (c->comm.world > 1) { set_err("context is banded: use octane_variational_flow_band_dev"); return OCTANE_EINVAL; }
+    begin_call(c);
+    return solve_dev(c, d_img1, d_img2, nx, ny, nc, p, d_u, d_v);
+}
+
+int octane_variational_flow_band_dev(octane_ctx* c, const float* d_img1, const float* d_img2, int nx, int ny, int nc,
+                                     const octane_params* p, float* d_u, float* d_v)
+{
+    if (!c) return OCTANE_EINVAL;
+    begin_call(c);
+    int rc = solve_dev(c, d_img1, d_img2, nx, ny, nc, p, d_u, d_v);
+    if (rc) return rc;
+    if (c->comm.world > 1) {          // halo check needs the device flag
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (c->h_scal->halo_err) { set_err("warp left the band halo: raise max_disp"); return OCTANE_EHALO; }
+    }
+    return OCTANE_OK;
+}
+
+int octane_variational_flow(octane_ctx* c, const float* img1, const float* img2, int nx, int ny, int nc,
+                            const octane_params* p, float* u, float* v)
+{
+    if (!c || !img1 || !img2 || !p || !u || !v) { set_err("null argument"); return OCTANE_EINVAL; }
+    if (c->comm.world > 1) { set_err("host-buffer entry points are single-GPU"); return OCTANE_EINVAL; }
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t n = (size_t)nx * ny, img_bytes = n * nc * sizeof(float), uv_bytes = n * sizeof(float);
+    int rc = ensure_stage(c, 2 * img_bytes + 2 * uv_bytes);
+    if (rc) return rc;
+    float* d_i1 = (float*)c->stage;
+    float* d_i2 = (float*)(c->stage + img_bytes);
+    float* d_u = (float*)(c->stage + 2 * img_bytes);
+    float* d_v = (float*)(c->stage + 2 * img_bytes + uv_bytes);
+    begin_call(c);
+    CUDA_OK(cudaMemcpyAsync(d_i1, img1, img_bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_i2, img2, img_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (p->first_guess) {
+        CUDA_OK(cudaMemcpyAsync(d_u, u, uv_bytes, cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaMemcpyAsync(d_v, v, uv_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    rc = solve_dev(c, d_i1, d_i2, nx, ny, nc, p, d_u, d_v);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(u, d_u, uv_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(v, d_v, uv_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return OCTANE_OK;
+}
+
+int octane_pix2uv_dev(octane_ctx* c, const octane_nav* nav, double t1, double t2, const float* d_u, const float* d_v,
+                      int nx, int ny, const octane_params* p, short* U, short* V, short* Ur, short* Vr)
+{
+    return pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, 0, ny, p, U, V, Ur, Vr);
+}
+
+int octane_pix2uv_band_dev(octane_ctx* c, const octane_nav* nav, double t1, double t2, const float* d_u,
+                           const float* d_v, int nx, int row0, int nrows, const octane_params* p,
+                           short* U, short* V, short* Ur, short* Vr)
+{
+    return pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, row0, nrows, p, U, V, Ur, Vr);
+}
+
+int octane_pix2uv(octane_ctx* c, const octane_nav* nav, double t1, double t2, const float* u, const float* v,
+                  int nx, int ny, const octane_params* p, short* U, short* V, short* Ur, short* Vr, float* dT)
+{
+    if (!c || !nav || !u || !v || !p || !U || !V || !Ur || !Vr) { set_err("null argument"); return OCTANE_EINVAL; }
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t n = (size_t)nx * ny, fb = n * sizeof(float), sb = n * sizeof(short);
+    int rc = ensure_stage(c, 2 * fb + 4 * sb);
+    if (rc) return rc;
+    float* d_u = (float*)c->stage;
+    float* d_v = (float*)(c->stage + fb);
+    short* d_s = (short*)(c->stage + 2 * fb);
+    begin_call(c);
+    CUDA_OK(cudaMemcpyAsync(d_u, u, fb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_v, v, fb, cudaMemcpyHostToDevice, c->stream));
+    rc = pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, 0, ny, p, d_s, d_s + n, d_s + 2 * n, d_s + 3 * n);
+    if (rc < 0) return rc;
+    CUDA_OK(cudaMemcpyAsync(U, d_s, sb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(V, d_s + n, sb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(Ur, d_s + 2 * n, sb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(Vr, d_s + 3 * n, sb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (dT) *dT = (float)(t2 - t1);           // :347
+    return rc;
+}
+
+int octane_optical_flow(octane_ctx* c, const float* img1, const float* img2, const float* cth, int nx, int ny, int nc,
+                        const octane_nav* nav, double t1, double t2, const octane_params* p,
+                        float* upix, float* vpix, short* U, short* V, short* Ur, short* Vr, short* ctp, float* dT)
+{
+    if (!c || !img1 || !img2 || !nav || !p || !upix || !vpix || !U || !V || !Ur || !Vr) { set_err("null argument"); return OCTANE_EINVAL; }
+    if (p->doCTH && (!cth || !ctp)) { set_err("doCTH needs cth and ctp"); return OCTANE_EINVAL; }
+    if (c->comm.world > 1) { set_err("host-buffer entry points are single-GPU"); return OCTANE_EINVAL; }
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t n = (size_t)nx * ny, ib = n * nc * sizeof(float), fb = n * sizeof(float), sb = n * sizeof(short);
+    int rc = ensure_stage(c, 2 * ib + 3 * fb + 5 * sb);
+    if (rc) return rc;
+    char* s = c->stage;
+    float* d_i1 = (float*)s; s += ib;
+    float* d_i2 = (float*)s; s += ib;
+    float* d_u = (float*)s; s += fb;
+    float* d_v = (float*)s; s += fb;
+    float* d_cth = (float*)s; s += fb;
+    short* d_s = (short*)s;
+    begin_call(c);
+    CUDA_OK(cudaMemcpyAsync(d_i1, img1, ib, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_i2, img2, ib, cudaMemcpyHostToDevice, c->stream));
+    if (p->first_guess) {
+        CUDA_OK(cudaMemcpyAsync(d_u, upix, fb, cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaMemcpyAsync(d_v, vpix, fb, cudaMemcpyHostToDevice, c->stream));
+    }
+    rc = solve_dev(c, d_i1, d_i2, nx, ny, nc, p, d_u, d_v);
+    if (rc) return rc;
+    if (p->doCTH) {                            // src/oct_optical_flow.cc:71-88
+        CUDA_OK(cudaMemcpyAsync(d_cth, cth, fb, cudaMemcpyHostToDevice, c->stream));
+        launch_ctp_pack(d_cth, d_s + 4 * n, n, p->ir == 1, c->stream);
+        c->launches++;
+        CUDA_OK(cudaMemcpyAsync(ctp, d_s + 4 * n, sb, cudaMemcpyDeviceToHost, c->stream));
+    }
+    int nrc = pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, 0, ny, p, d_s, d_s + n, d_s + 2 * n, d_s + 3 * n);
+    if (nrc < 0) return nrc;
+    CUDA_OK(cudaMemcpyAsync(upix, d_u, fb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(vpix, d_v, fb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(U, d_s, sb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(V, d_s + n, sb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(Ur, d_s + 2 * n, sb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(Vr, d_s + 3 * n, sb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (dT) *dT = (float)(t2 - t1);
+    return nrc;
+}
+
+// ---- band planning / NCCL bootstrap ----------------------------------------------------------
+int octane_band_plan(int nx, int ny, const octane_params* p, int rank, int world, int* own0, int* own1, int* in0, int* in1)
+{
+    if (!p || rank < 0 || world < 1 || rank >= world) { set_err("invalid argument"); return OCTANE_EINVAL; }
+    Plan pl;
+    int rc = make_plan(pl, nx, ny, 1, *p, rank, world);
+    if (rc) return rc;
+    if (own0) *own0 = pl.lv.back().own0;
+    if (own1) *own1 = pl.lv.back().own1;
+    if (in0) *in0 = pl.in0;
+    if (in1) *in1 = pl.in1;
+    return OCTANE_OK;
+}
+
+int octane_comm_unique_id(char id[128])
+{
+    if (!id) return OCTANE_EINVAL;
+    if (comm_unique_id(id)) { set_err("%s", comm_last_error()); return OCTANE_ECOMM; }
+    return OCTANE_OK;
+}
+
+int octane_comm_init(octane_ctx* c, const char id[128], int rank, int world)
+{
+    if (!c || !id || rank < 0 || world < 1 || rank >= world) { set_err("invalid argument"); return OCTANE_EINVAL; }
+    CUDA_OK(cudaSetDevice(c->device));
+    c->plan_valid = false;
+    destroy_graphs(c);
+    comm_destroy(&c->comm);
+    if (world == 1) return OCTANE_OK;
+    if (comm_init(&c->comm, id, rank, world)) { set_err("%s", comm_last_error()); return OCTANE_ECOMM; }
+    return OCTANE_OK;
+}
+
+int octane_comm_rank(octane_ctx* c, int* rank, int* world)
+{
+    if (!c) return OCTANE_EINVAL;
+    if (rank) *rank = c->comm.rank;
+    if (world) *world = c->comm.world;
+    return OCTANE_OK;
+}
+
+// ---- stage entry points (parity tests) -----------------------------------------------------
+static Geom dense_geom(int nx, int ny)
+{
+    Geom g; g.nx = nx; g.ny = ny; g.pitch = nx; g.j0 = 0; g.rows = ny; g.plane = (long long)nx * ny;
+    return g;
+}
+
+int octane_stage_blur_decimate(octane_ctx* c, const float* d_img, int nx, int ny, int nc, float factor, float* d_out)
+{
+    if (!c || !d_img || !d_out) return OCTANE_EINVAL;
+    CUDA_OK(cudaSetDevice(c->device));
+    int rc = ensure_small(c, c->sm_count * 16); if (rc) return rc;
+    int nxx, nyy;
+    zoom_size(nx, ny, factor, &nxx, &nyy);
+    const int R = filter_radius(factor);
+    Geom gs = dense_geom(nx, ny), gd = dense_geom(nxx, nyy);
+    launch_fill_gk(c->d_gk, factor, R, c->stream);
+    launch_blur_decimate(d_img, gs, d_out, gd, 0, nyy, factor, c->d_gk, R, 1.f, nc, c->stream);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return OCTANE_OK;
+}
+
+int octane_stage_gradient(octane_ctx* c, const float* d_f, int xi, int yi, int nc, float* d_gx, float* d_gy)
+{
+    if (!c || !d_f || !d_gx || !d_gy) return OCTANE_EINVAL;
+    CUDA_OK(cudaSetDevice(c->device));
+    launch_gradient(d_f, d_gx, d_gy, dense_geom(xi, yi), 0, yi, nc, c->stream);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return OCTANE_OK;
+}
+
+int octane_stage_zoom_in(octane_ctx* c, const float* d_flow, int nx, int ny, int nxx, int nyy, float sf, float* d_out)
+{
+    if (!c || !d_flow || !d_out) return OCTANE_EINVAL;
+    CUDA_OK(cudaSetDevice(c->device));
+    launch_zoom_in(d_flow, dense_geom(nx, ny), d_out, dense_geom(nxx, nyy), 0, nyy, sf, c->stream);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return OCTANE_OK;
+}
+
+// The build and PCG stages run on the pitched workspace exactly as the full solve does:
+// dense inputs are copied in, the level's kernels run, dense outputs are copied out.
+static int stage_prepare(octane_ctx* c, int xi, int yi, int nc, const octane_params* p)
+{
+    octane_params q = *p;
+    q.kiters = 1;             // a single level of size xi x yi
+    return prepare(c, xi, yi, nc, q);
+}
+
+static int copy_in(octane_ctx* c, float* dst, const float* src, const Geom& g, int nplanes)
+{
+    const size_t w = (size_t)g.nx * sizeof(float), dp = (size_t)g.pitch * sizeof(float);
+    for (int k = 0; k < nplanes; k++)
+        CUDA_OK(cudaMemcpy2DAsync(dst + (size_t)k * g.plane, dp, src + (size_t)k * g.nx * g.ny, w, w, g.ny,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+    return OCTANE_OK;
+}
+static int copy_out(octane_ctx* c, float* dst, const float* src, const Geom& g)
+{
+    const size_t w = (size_t)g.nx * sizeof(float), dp = (size_t)g.pitch * sizeof(float);
+    CUDA_OK(cudaMemcpy2DAsync(dst, w, src, dp, w, g.ny, cudaMemcpyDeviceToDevice, c->stream));
+    return OCTANE_OK;
+}
+
+int octane_stage_build(octane_ctx* c, const float* d_u, const float* d_v, const float* d_uh, const float* d_vh,
+                       const float* d_g1, const float* d_g2, int xi, int yi, int nc, const octane_params* p,
+                       float lambdac_level, int gnc, float* d_coef, float* d_bu, float* d_bv)
+{
+    if (!c || !d_u || !d_v || !d_g1 || !d_g2 || !p || !d_coef || !d_bu || !d_bv) return OCTANE_EINVAL;
+    octane_params q = *p;
+    q.first_guess = (d_uh && d_vh) ? 1 : 0;
+    int rc = stage_prepare(c, xi, yi, nc, &q); if (rc) return rc;
+    Buffers& B = c->buf;
+    const Geom& g = c->plan.lv[0].g;
+    cudaStream_t st = c->stream;
+    if ((rc = copy_in(c, B.img1, d_g1, g, nc))) return rc;
+    if ((rc = copy_in(c, B.img2, d_g2, g, nc))) return rc;
+    if ((rc = copy_in(c, B.u, d_u, g, 1))) return rc;
+    if ((rc = copy_in(c, B.v, d_v, g, 1))) return rc;
+    if (q.first_guess) { if ((rc = copy_in(c, B.uh, d_uh, g, 1))) return rc; if ((rc = copy_in(c, B.vh, d_vh, g, 1))) return rc; }
+    launch_gradient(B.img1, B.g1x, B.g1y, g, 0, yi, nc, st);
+    launch_gradient(B.img2, B.g2x, B.g2y, g, 0, yi, nc, st);
+    launch_gradient(B.g2x, B.g2xx, B.g2xy, g, 0, yi, nc, st);
+    launch_gradient(B.g2y, B.g2xy, B.g2yy, g, 0, yi, nc, st);
+    LevelFields f;
+    f.g1 = B.img1; f.g1x = B.g1x; f.g1y = B.g1y;
+    f.g2 = B.img2; f.g2x = B.g2x; f.g2y = B.g2y; f.g2xx = B.g2xx; f.g2xy = B.g2xy; f.g2yy = B.g2yy;
+    f.u = B.u; f.v = B.v;
+    f.uh = (q.first_guess && lambdac_level != 0.f) ? B.uh : nullptr;
+    f.vh = (q.first_guess && lambdac_level != 0.f) ? B.vh : nullptr;
+    BuildParams bp;
+    bp.alpha = p->alpha; bp.lambdadalpha = p->lambda / p->alpha; bp.lambdac = lambdac_level;
+    bp.dozim = p->dozim != 0; bp.nchan = nc; bp.tol = 0.0001 * 0.0001; bp.al1 = 1. - 0.5 * gnc;
+    launch_build(f, B.pcg, g, 0, yi, 0, yi, bp, 0, st);
+    for (int k = 0; k < 7; k++) if ((rc = copy_out(c, d_coef + (size_t)k * xi * yi, B.pcg.coef[k], g))) return rc;
+    if ((rc = copy_out(c, d_bu, B.pcg.ru, g))) return rc;
+    if ((rc = copy_out(c, d_bv, B.pcg.rv, g))) return rc;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(st));
+    return OCTANE_OK;
+}
+
+// seeds the PCG scalars from (coef, b) like the tail of the build kernel does
+__global__ void k_seed_scalars(PcgBuffers b, Geom g, float tol)
+{
+    __shared__ double red[2 * 32];
+    double acc[2] = { 0.0, 0.0 };
+    for (int j = 0; j < g.ny; j++)
+        for (int i = threadIdx.x; i < g.nx; i += blockDim.x) {
+            const size_t l = g.at(i, j);
+            const float bu = b.ru[l], bv = b.rv[l];
+            const float mu = 1. / b.coef[0][l], mv = 1. / b.coef[2][l];
+            acc[0] += (double)(bu * bu) + (double)(bv * bv);
+            acc[1] += (double)(bu * (mu * bu)) + (double)(bv * (mv * bv));
+        }
+    block_sum<2>(acc, red);
+    if (threadIdx.x == 0) {
+        PcgScalars* s = b.scal;
+        s->rr = (float)acc[0]; s->rz = (float)acc[1]; s->rz_old = 0.f; s->pAp = 0.f;
+        s->tol = tol; s->its = 0; s->done = !((float)acc[0] > tol);
+    }
+}
+
+int octane_stage_pcg(octane_ctx* c, const float* d_coef, const float* d_bu, const float* d_bv, int xi, int yi,
+                     int iters, float tol, float* d_xu, float* d_xv, int* iterations)
+{
+    if (!c || !d_coef || !d_bu || !d_bv || !d_xu || !d_xv) return OCTANE_EINVAL;
+    octane_params q;
+    octane_params_default(&q);
+    q.cgiters = iters;
+    int rc = stage_prepare(c, xi, yi, 1, &q); if (rc) return rc;
+    Buffers& B = c->buf;
+    const Level& L = c->plan.lv[0];
+    const Geom& g = L.g;
+    cudaStream_t st = c->stream;
+    for (int k = 0; k < 7; k++) if ((rc = copy_in(c, B.pcg.coef[k], d_coef + (size_t)k * xi * yi, g, 1))) return rc;
+    if ((rc = copy_in(c, B.pcg.ru, d_bu, g, 1))) return rc;
+    if ((rc = copy_in(c, B.pcg.rv, d_bv, g, 1))) return rc;
+    k_seed_scalars<<<1, 1024, 0, st>>>(B.pcg, g, tol);
+    CUDA_OK(cudaMemsetAsync(B.u, 0, (size_t)g.plane * sizeof(float), st));
+    CUDA_OK(cudaMemsetAsync(B.v, 0, (size_t)g.plane * sizeof(float), st));
+    begin_call(c);
+    rc = run_pcg(c, L, 0, 0); if (rc) return rc;
+    launch_update_uv(B.u, B.v, B.pcg.xu, B.pcg.xv, g, 0, yi, c->d_scal, c->d_its, c->sm_count, st);   // u = 0 + x
+    if ((rc = copy_out(c, d_xu, B.u, g))) return rc;
+    if ((rc = copy_out(c, d_xv, B.v, g))) return rc;
+    CUDA_OK(cudaMemcpyAsync(c->h_its, c->d_its, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (iterations) *iterations = c->h_its[0];
+    return OCTANE_OK;
+}
+
+}  // extern "C"

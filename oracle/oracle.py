@@ -1,0 +1,201 @@
+"""ctypes view of the CHECKERS (test infrastructure; never imported by the
+product package octane_b200):
+
+  liboracle.so           CPU restatement, oracle/oct_oracle.c
+  _ref/libref_cpu.so     reference CPU stages compiled in place
+  _ref/libref_cuda.so    reference CUDA path recompiled for sm_100 (needs a GPU)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64 = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i16 = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+_i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+class OracleParams(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("lambda_", C.c_double), ("lambdac", C.c_double),
+                ("scaleF", C.c_double), ("kiters", C.c_int), ("liters", C.c_int),
+                ("cgiters", C.c_int), ("dozim", C.c_int)]
+
+
+class OracleNav(C.Structure):
+    _fields_ = [("pph", C.c_double), ("req", C.c_double), ("rpol", C.c_double), ("lam0", C.c_double),
+                ("xScale", C.c_float), ("xOffset", C.c_float), ("yScale", C.c_float), ("yOffset", C.c_float),
+                ("g2xOffset", C.c_float), ("g2yOffset", C.c_float),
+                ("lat1", C.c_float), ("lon1", C.c_float), ("lon0", C.c_float), ("R", C.c_float),
+                ("minX", C.c_int), ("minY", C.c_int)]
+
+
+class RefParams(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("lambda_", C.c_double), ("lambdac", C.c_double),
+                ("scaleF", C.c_double), ("scsig", C.c_double),
+                ("kiters", C.c_int), ("liters", C.c_int), ("cgiters", C.c_int), ("dozim", C.c_int),
+                ("setdevice", C.c_int), ("pixuv", C.c_int), ("dopolar", C.c_int), ("domerc", C.c_int),
+                ("dososm", C.c_int), ("rad", C.c_int), ("srad", C.c_int), ("doCTH", C.c_int),
+                ("ir", C.c_int), ("dofirstguess", C.c_int)]
+
+
+RefNav = OracleNav  # same field order in oracle/ref_driver.cc
+
+
+def params(alpha=5.0, lambda_=1.0, lambdac=0.0, scaleF=0.5, kiters=4, liters=3, cgiters=30, dozim=1):
+    return OracleParams(alpha, lambda_, lambdac, scaleF, kiters, liters, cgiters, dozim)
+
+
+def ref_params(alpha=5.0, lambda_=1.0, lambdac=0.0, scaleF=0.5, kiters=4, liters=3, cgiters=30, dozim=1,
+               pixuv=0, dopolar=0, domerc=0, dososm=0, rad=2, srad=2, doCTH=0, ir=0, dofirstguess=0):
+    return RefParams(alpha, lambda_, lambdac, scaleF, 400.0, kiters, liters, cgiters, dozim, 0,
+                     pixuv, dopolar, domerc, dososm, rad, srad, doCTH, ir, dofirstguess)
+
+
+def goes_nav(xScale, yScale, xOffset, yOffset, pph=35786023.0, req=6378137.0, rpol=6356752.31414,
+             lon0_deg=-75.0, minX=0, minY=0, g2xOffset=None, g2yOffset=None, cls=OracleNav):
+    lam0 = lon0_deg * (3.14159265 / 180.0)
+    return cls(pph, req, rpol, lam0, xScale, xOffset, yScale, yOffset,
+               xOffset if g2xOffset is None else g2xOffset, yOffset if g2yOffset is None else g2yOffset,
+               0.0, 0.0, 0.0, 6371000.0, minX, minY)
+
+
+def build(ref: bool = True) -> None:
+    subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so"] + (["ref"] if ref else []))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        L = C.CDLL(path)
+        L.oracle_variational_flow.argtypes = [_f32, _f32, C.c_int, C.c_int, C.c_int, C.POINTER(OracleParams),
+                                              _f32, _f32, C.c_void_p]
+        L.oracle_blur_decimate.argtypes = [_f32, C.c_int, C.c_int, C.c_int, C.c_float, _f32]
+        L.oracle_gradient.argtypes = [_f32, _f32, _f32, C.c_int, C.c_int, C.c_int]
+        L.oracle_zoom_in.argtypes = [_f32, _f32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+        L.oracle_zoom_size.argtypes = [C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.oracle_level_factor.argtypes = [C.c_double, C.c_int, C.c_int]
+        L.oracle_level_factor.restype = C.c_float
+        L.oracle_filter_radius.argtypes = [C.c_float]
+        L.oracle_fill_gk.argtypes = [_f32, C.c_float, C.c_int]
+        L.oracle_build.argtypes = [_f32, _f32, C.c_void_p, C.c_void_p] + [_f32] * 9 + \
+            [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_float, C.c_int, C.c_int, _f32, _f32, _f32]
+        L.oracle_apply.argtypes = [_f32, _f32, _f32, C.c_int, C.c_int, _f32, _f32]
+        L.oracle_pcg.argtypes = [_f32, _f32, _f32, _f32, _f32, C.c_int, C.c_int, C.c_int, C.c_float, _f32]
+        L.oracle_pix2uv.argtypes = [C.POINTER(OracleNav), C.c_double, C.c_double, _f32, _f32, C.c_int, C.c_int,
+                                    C.c_int, _i16, _i16, _i16, _i16, C.POINTER(C.c_float)]
+        L.oracle_pix2uv_ms.argtypes = [C.POINTER(OracleNav), C.c_double, C.c_double, _f32, _f32, C.c_int, C.c_int,
+                                       C.c_int, _f64, _f64]
+        _lib = L
+    return _lib
+
+
+def level_dims(nx, ny, kiters=4, scaleF=0.5):
+    L = lib()
+    out = []
+    for k in range(kiters):
+        f = L.oracle_level_factor(scaleF, kiters, k)
+        a, b = C.c_int(), C.c_int()
+        L.oracle_zoom_size(nx, ny, f, C.byref(a), C.byref(b))
+        out.append((a.value, b.value))
+    return out
+
+
+def variational_flow(img1, img2, p=None, u0=None, v0=None, nc=1):
+    """img*: (nc*)ny x nx float32. Returns (u, v, cg_its)."""
+    p = p or params()
+    img1 = np.ascontiguousarray(img1, np.float32)
+    img2 = np.ascontiguousarray(img2, np.float32)
+    ny, nx = img1.shape[-2:]
+    u = np.zeros((ny, nx), np.float32) if u0 is None else np.array(u0, np.float32, copy=True)
+    v = np.zeros((ny, nx), np.float32) if v0 is None else np.array(v0, np.float32, copy=True)
+    its = np.zeros(p.kiters * 3 * p.liters, np.int32)
+    lib().oracle_variational_flow(img1, img2, nx, ny, nc, C.byref(p), u, v, its.ctypes.data)
+    return u, v, its
+
+
+def pix2uv(nav, t1, t2, u, v, flags=0):
+    u = np.ascontiguousarray(u, np.float32); v = np.ascontiguousarray(v, np.float32)
+    ny, nx = u.shape
+    o = [np.zeros((ny, nx), np.int16) for _ in range(4)]
+    dT = C.c_float()
+    rc = lib().oracle_pix2uv(C.byref(nav), t1, t2, u, v, nx, ny, flags, *o, C.byref(dT))
+    return (*o, dT.value, rc)
+
+
+def pix2uv_ms(nav, t1, t2, u, v, flags=0):
+    u = np.ascontiguousarray(u, np.float32); v = np.ascontiguousarray(v, np.float32)
+    ny, nx = u.shape
+    a = np.zeros((ny, nx)); b = np.zeros((ny, nx))
+    lib().oracle_pix2uv_ms(C.byref(nav), t1, t2, u, v, nx, ny, flags, a, b)
+    return a, b
+
+
+# ---- the reference itself -------------------------------------------------
+_ref_cpu = None
+_ref_cuda = None
+
+
+def ref_cpu():
+    global _ref_cpu
+    if _ref_cpu is None:
+        L = C.CDLL(os.path.join(HERE, "_ref", "libref_cpu.so"))
+        L.ref_patch_match.argtypes = [_f32, _f32, _f32, _f32, C.c_int, C.c_int, C.POINTER(RefParams)]
+        L.ref_zoom_out.argtypes = [_f64, _f64, C.c_int, C.c_int, C.c_double]
+        L.ref_zoom_in.argtypes = [_f64, _f64, C.c_int, C.c_int, C.c_int, C.c_int]
+        _ref_cpu = L
+    return _ref_cpu
+
+
+def ref_cuda():
+    global _ref_cuda
+    if _ref_cuda is None:
+        L = C.CDLL(os.path.join(HERE, "_ref", "libref_cuda.so"))
+        L.ref_variational.argtypes = [_f32, _f32, C.c_int, C.c_int, C.c_int, _f32, _f32, C.POINTER(RefParams)]
+        L.ref_pix2uv.argtypes = [C.POINTER(RefNav), C.c_double, C.c_double, _f32, _f32, C.c_int, C.c_int,
+                                 C.POINTER(RefParams), _i16, _i16, _i16, _i16, C.POINTER(C.c_float)]
+        L.ref_optical_flow.argtypes = [_f32, _f32, C.c_void_p, C.c_int, C.c_int, C.POINTER(RefNav),
+                                       C.c_double, C.c_double, C.POINTER(RefParams),
+                                       _f32, _f32, _i16, _i16, _i16, _i16, C.c_void_p, C.POINTER(C.c_float)]
+        L.ref_patch_match.argtypes = [_f32, _f32, _f32, _f32, C.c_int, C.c_int, C.POINTER(RefParams)]
+        _ref_cuda = L
+    return _ref_cuda
+
+
+def ref_variational(img1, img2, rp=None, u0=None, v0=None, nc=1):
+    rp = rp or ref_params()
+    img1 = np.ascontiguousarray(img1, np.float32); img2 = np.ascontiguousarray(img2, np.float32)
+    ny, nx = img1.shape[-2:]
+    u = np.zeros((ny, nx), np.float32) if u0 is None else np.array(u0, np.float32, copy=True)
+    v = np.zeros((ny, nx), np.float32) if v0 is None else np.array(v0, np.float32, copy=True)
+    ref_cuda().ref_variational(img1, img2, nx, ny, nc, u, v, C.byref(rp))
+    return u, v
+
+
+def ref_pix2uv(nav, t1, t2, u, v, rp=None):
+    rp = rp or ref_params()
+    u = np.ascontiguousarray(u, np.float32); v = np.ascontiguousarray(v, np.float32)
+    ny, nx = u.shape
+    o = [np.zeros((ny, nx), np.int16) for _ in range(4)]
+    dT = C.c_float()
+    ref_cuda().ref_pix2uv(C.byref(nav), t1, t2, u, v, nx, ny, C.byref(rp), *o, C.byref(dT))
+    return (*o, dT.value)
+
+
+def ref_patch_match(img1, img2, rp=None):
+    rp = rp or ref_params(dososm=1)
+    img1 = np.ascontiguousarray(img1, np.float32); img2 = np.ascontiguousarray(img2, np.float32)
+    ny, nx = img1.shape
+    u = np.zeros((ny, nx), np.float32); v = np.zeros((ny, nx), np.float32)
+    ref_cpu().ref_patch_match(img1, img2, u, v, nx, ny, C.byref(rp))
+    return u, v

@@ -1,0 +1,150 @@
+// oracle/ref_driver.cc -- TEST INFRASTRUCTURE, not product code.
+//
+// In-memory driver around the UNMODIFIED reference objects.  The recipe in
+// oracle/Makefile compiles the reference sources where they lie under
+// /root/reference (nothing is copied into this repo) and links them with this
+// file into oracle/_ref/libref_cuda.so (GPU stages + dispatcher) and
+// oracle/_ref/libref_cpu.so (CPU-only stages).  The driver replaces the
+// NetCDF readers: it fills the reference's own Image / GOESVar / OFFlags
+// objects from flat arrays and calls the reference entry points
+//   oct_variational_optical_flow   src/oct_variational_optical_flow.cu:1213
+//   oct_pix2uv_cuda                src/oct_pix2uv_cuda.cu:265
+//   oct_optical_flow               src/oct_optical_flow.cc:21
+//   oct_patch_match_optical_flow   src/oct_patch_match_optical_flow.cc:56
+//   oct_zoom_out / oct_zoom_in     src/oct_zoom.cc:17,154
+// Only tests/, __graft_entry__.smoke() and bench.py's baseline legs load it.
+#include <cstring>
+#include <string>
+#include "image.h"
+#include "goesread.h"
+#include "offlags.h"
+
+void oct_patch_match_optical_flow(float*, float*, float*, float*, int, int, OFFlags);
+void oct_zoom_out(double*, double*, int, int, double, int);
+void oct_zoom_in(double*, double*, int, int, int, int);
+#ifdef REF_WITH_CUDA
+void oct_variational_optical_flow(Image, Image, float*, float*, float*, int, int, int, OFFlags);
+void oct_pix2uv_cuda(GOESVar&, double, float*, float*, short*, short*, short*, short*, OFFlags);
+int oct_optical_flow(GOESVar&, GOESVar&, OFFlags&);
+#endif
+
+// Flat parameter block shared with Python (ctypes); order matters.
+struct RefParams {
+    double alpha, lambda, lambdac, scaleF, scsig;
+    int kiters, liters, cgiters, dozim, setdevice;
+    int pixuv, dopolar, domerc, dososm, rad, srad, doCTH, ir, dofirstguess;
+};
+struct RefNav {
+    double pph, req, rpol, lam0;
+    float xScale, xOffset, yScale, yOffset, g2xOffset, g2yOffset;
+    float lat1, lon1, lon0, R;
+    int minX, minY;
+};
+
+static void defaults(OFFlags& a, const RefParams* p)
+{
+    // every field main.cc:53-108 sets, then the caller's overrides
+    a.farn = 0; a.pixuv = p->pixuv; a.dosrsal = 0; a.dopolar = p->dopolar; a.domerc = p->domerc;
+    a.ftype = "GOES"; a.fpyr_scale = 0.5; a.flevels = 2; a.fwinsize = 20; a.fiterations = 5;
+    a.poly_n = 10; a.poly_sigma = 0.5; a.uif = 0; a.fg = 1; a.dofirstguess = p->dofirstguess;
+    a.ir = p->ir; a.dososm = p->dososm; a.dointerp = 0; a.docorn = 0; a.rad = p->rad; a.srad = p->srad;
+    a.lambda = p->lambda; a.alpha = p->alpha; a.filtsigma = 3.; a.scaleF = p->scaleF;
+    a.kiters = p->kiters; a.alpha2 = 20.; a.lambdac = p->lambdac; a.liters = p->liters;
+    a.cgiters = p->cgiters; a.miters = 5; a.scsig = p->scsig; a.interpcth = 1; a.deltat = 60.;
+    a.doc2 = 0; a.doahi = 0; a.doc3 = 0; a.doinv = 0; a.doctt = 0; a.doCTH = p->doCTH;
+    a.dozim = p->dozim; a.outraw = a.outctp = a.outrad = a.outnav = true; a.setdevice = p->setdevice;
+    a.putinterp = 0; a.oftype = 0; a.setnorms = 0;
+    a.NormMax = a.NormMin = a.NormMax2 = a.NormMin2 = a.NormMax3 = a.NormMin3 = 0.f;
+    a.setNormMax = a.setNormMin = a.setNormMax2 = a.setNormMin2 = a.setNormMax3 = a.setNormMin3 = true;
+}
+
+static void fill_nav(GOESNAVVar& n, const RefNav* s, int nx, int ny)
+{
+    std::memset(&n, 0, sizeof(n));
+    n.pph = s->pph; n.req = s->req; n.rpol = s->rpol; n.lam0 = s->lam0;
+    n.xScale = s->xScale; n.xOffset = s->xOffset; n.yScale = s->yScale; n.yOffset = s->yOffset;
+    n.g2xOffset = s->g2xOffset; n.g2yOffset = s->g2yOffset;
+    n.lat1 = s->lat1; n.lon1 = s->lon1; n.lon0 = s->lon0; n.R = s->R;
+    n.minX = s->minX; n.minY = s->minY; n.nx = nx; n.ny = ny;
+}
+
+extern "C" {
+
+int ref_patch_match(const float* g1, const float* g2, float* u, float* v, int nx, int ny,
+                    const RefParams* p)
+{
+    OFFlags a; defaults(a, p);
+    oct_patch_match_optical_flow(const_cast<float*>(g1), const_cast<float*>(g2), u, v, nx, ny, a);
+    return 0;
+}
+
+int ref_zoom_out(const double* in, double* out, int nx, int ny, double factor)
+{
+    oct_zoom_out(const_cast<double*>(in), out, nx, ny, factor, 0);
+    return 0;
+}
+
+int ref_zoom_in(const double* in, double* out, int nx, int ny, int nxx, int nyy)
+{
+    oct_zoom_in(const_cast<double*>(in), out, nx, ny, nxx, nyy);
+    return 0;
+}
+
+#ifdef REF_WITH_CUDA
+int ref_variational(const float* g1, const float* g2, int nx, int ny, int nc,
+                    float* u, float* v, const RefParams* p)
+{
+    OFFlags a; defaults(a, p);
+    Image i1(ny, nx, nc), i2(ny, nx, nc);
+    i1.data = const_cast<float*>(g1);
+    i2.data = const_cast<float*>(g2);
+    float cth = 0.f;
+    oct_variational_optical_flow(i1, i2, &cth, u, v, nx, ny, nc, a);
+    return 0;
+}
+
+int ref_pix2uv(const RefNav* nav, double t1, double t2, const float* u, const float* v,
+               int nx, int ny, const RefParams* p,
+               short* ur, short* vr, short* ur2, short* vr2, float* dT)
+{
+    OFFlags a; defaults(a, p);
+    GOESVar g;
+    fill_nav(g.nav, nav, nx, ny);
+    g.t = t1;
+    oct_pix2uv_cuda(g, t2, const_cast<float*>(u), const_cast<float*>(v), ur, vr, ur2, vr2, a);
+    *dT = g.dT;
+    return 0;
+}
+
+// Whole dispatcher (zero first guess -> solver -> CTP pack -> navigation).
+// Output arrays are the reference's own new[] blocks; they are copied out and
+// left to the process (the reference never frees them either).
+int ref_optical_flow(const float* g1, const float* g2, const float* cth, int nx, int ny,
+                     const RefNav* nav, double t1, double t2, const RefParams* p,
+                     float* upix, float* vpix, short* ur, short* vr, short* ur2, short* vr2,
+                     short* ctp, float* dT)
+{
+    OFFlags a; defaults(a, p);
+    GOESVar d1, d2;
+    fill_nav(d1.nav, nav, nx, ny);
+    fill_nav(d2.nav, nav, nx, ny);
+    d1.t = t1; d2.t = t2;
+    d1.data.setdims(ny, nx, 1); d2.data.setdims(ny, nx, 1);
+    d1.data.data = const_cast<float*>(g1);
+    d2.data.data = const_cast<float*>(g2);
+    d1.CTHVal = const_cast<float*>(cth);
+    oct_optical_flow(d1, d2, a);
+    size_t n = (size_t)nx * ny;
+    std::memcpy(upix, d1.uPix, n * sizeof(float));
+    std::memcpy(vpix, d1.vPix, n * sizeof(float));
+    std::memcpy(ur, d1.uVal, n * sizeof(short));
+    std::memcpy(vr, d1.vVal, n * sizeof(short));
+    std::memcpy(ur2, d1.uVal2, n * sizeof(short));
+    std::memcpy(vr2, d1.vVal2, n * sizeof(short));
+    if (a.doCTH == 1 && ctp) std::memcpy(ctp, d1.CTP, n * sizeof(short));
+    *dT = d1.dT;
+    return 0;
+}
+#endif
+
+}  // extern "C"
