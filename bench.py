@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- flow Mpix/s of the dense variational optical-flow path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload fulldisk|conus|meso]
+    python bench.py --impl reference ...          # the reference's own CPU flow path
+
+One "step" = one pass of the hot path over one synthetic image pair:
+pyramid -> (build + Jacobi-PCG) x kiters*3*liters -> prolongation -> pix2uv
+navigation.  `value` is timed with the pair already resident in HBM (CUDA
+events on the context's stream); `e2e` is the same metric through the C-ABI
+host-buffer entry point octane_optical_flow (pinned host inputs, H2D and D2H
+inside the timed region).  N > 1 shards the pair across ranks as row bands
+(halo exchange + scalar all-reduce over NCCL): total work is fixed -> "strong".
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nx, ny, sector, limb taper)
+    "fulldisk": (21696, 21696, "fulldisk_0.5km", True),
+    "conus": (10000, 6000, "conus_0.5km", False),
+    "meso": (2000, 2000, "meso_0.5km", False),
+    "meso500": (500, 500, "meso_2km", False),
+}
+METRIC = "flow Mpix/s"
+B_PASS1, B_PASS2 = 60.0, 64.0      # algorithmic bytes per pixel per launch
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        self.t.join(timeout=5)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, c[3:7]):
+                if val == "Active":
+                    reasons.add(nm)
+        # samples under load only (idle samples at the edges read the idle clock)
+        load = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(nx, ny, sector, seed, size):
+    """Bounded sample for the CPU arms: a size x size crop at the scene centre (same generator)."""
+    import torch
+
+    from octane_b200 import synthetic as S
+    sx, sy = min(size, nx), min(size, ny)
+    r0 = (ny - sy) // 2
+    a, b = S.make_pair_torch(nx, ny, seed, "cpu", rows=(r0, r0 + sy), limb_taper=False)
+    c0 = (nx - sx) // 2
+    i1 = a[:, c0:c0 + sx].contiguous().numpy()
+    i2 = b[:, c0:c0 + sx].contiguous().numpy()
+    return i1, i2, c0, r0
+
+
+def run_cpu_port(nx, ny, sector, seed, size=2048):
+    """cpu_baseline kind 'port': the CPU oracle (OpenMP, all host cores) on a bounded sample."""
+    import numpy as np
+
+    from octane_b200 import synthetic as S
+    from oracle import oracle as O
+    i1, i2, c0, r0 = cpu_sample(nx, ny, sector, seed, size)
+    xs, ys, xo, yo, dt = S.SECTORS[sector]
+    nav = O.goes_nav(xs, ys, xo, yo, minX=c0, minY=r0)
+    t = time.perf_counter()
+    u, v, _ = O.variational_flow(i1, i2)
+    O.pix2uv(nav, 0.0, dt, u, v)
+    sec = time.perf_counter() - t
+    n = i1.shape[0] * i1.shape[1]
+    return {"value": n / sec / 1e6, "unit": "Mpix/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{i1.shape[1]}x{i1.shape[0]} centre crop of the workload, 1 pair, variational oracle + pix2uv, OpenMP",
+            "seconds": sec}
+
+
+def run_ref_cuda(nx, ny, sector, seed, size=2000):
+    """The reference's own CUDA path recompiled for sm_100 (oracle/_ref), bounded sample, 1 host thread."""
+    from octane_b200 import synthetic as S
+    from oracle import oracle as O
+    import numpy as np
+    i1, i2, c0, r0 = cpu_sample(nx, ny, sector, seed, size)
+    xs, ys, xo, yo, dt = S.SECTORS[sector]
+    nav = O.goes_nav(xs, ys, xo, yo, minX=c0, minY=r0)
+    sy, sx = i1.shape
+    L = O.ref_cuda()
+    import ctypes as C
+    outs = [np.zeros((sy, sx), np.int16) for _ in range(4)]
+    up = np.zeros((sy, sx), np.float32); vp = np.zeros((sy, sx), np.float32)
+    dT = C.c_float()
+    rp = O.ref_params()
+    best = None
+    for _ in range(2):       # first call pays CUDA context + managed-memory setup
+        t = time.perf_counter()
+        L.ref_optical_flow(i1, i2, None, sx, sy, C.byref(nav), 0.0, dt, C.byref(rp), up, vp, *outs, None, C.byref(dT))
+        sec = time.perf_counter() - t
+        best = sec if best is None else min(best, sec)
+    return {"value": sx * sy / best / 1e6, "unit": "Mpix/s", "sample": f"{sx}x{sy} centre crop, best of 2, whole oct_optical_flow() "
+            "call (managed-memory migration and host loops included)", "seconds": best, "host_threads": 1}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the flow path
+    (oct_patch_match_optical_flow, its -sosm solver, compiled unmodified into
+    oracle/_ref/libref_cpu.so) on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx, ny, sector, _ = WORKLOADS[args.workload]
+    import numpy as np
+
+    from oracle import oracle as O
+    size = args.ref_size
+    i1, i2, c0, r0 = cpu_sample(nx, ny, sector, args.seed, size)
+    n = i1.shape[0] * i1.shape[1]
+    kind = "reference"
+    try:
+        O.ref_cpu()
+        fn = lambda: O.ref_patch_match(i1, i2)                 # noqa: E731
+        what = "oct_patch_match_optical_flow rad=2 srad=2 (reference objects, single-threaded code)"
+        cores = 1
+    except OSError:
+        kind = "port"
+        fn = lambda: O.variational_flow(i1, i2)                # noqa: E731
+        what = "variational CPU oracle (reference objects absent)"
+        cores = os.cpu_count()
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        fn()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    sec = (time.perf_counter() - t) / args.steps
+    v = n / sec / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload} {nx}x{ny}", "sample": f"{i1.shape[1]}x{i1.shape[0]} centre crop"},
+            "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": kind,
+                             "sample": f"{i1.shape[1]}x{i1.shape[0]} centre crop per step; {what}"},
+            "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "host_cores_available": os.cpu_count()}
+    if args.ref_cuda:
+        try:
+            line["ref_cuda_sm100"] = run_ref_cuda(nx, ny, sector, args.seed)
+        except Exception as e:   # no GPU / library absent
+            line["ref_cuda_sm100"] = {"unavailable": str(e)[:120]}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fulldisk", choices=sorted(WORKLOADS))
+    ap.add_argument("--seed", type=int, default=4)
+    ap.add_argument("--ref-size", type=int, default=1000, help="crop edge of the --impl reference sample")
+    ap.add_argument("--ref-cuda", action="store_true", help="also time the reference CUDA build (sm_100 recompile)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--max-disp", type=int, default=64)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+
+    import octane_b200 as ob
+    from octane_b200 import synthetic as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    nx, ny, sector, taper = WORKLOADS[args.workload]
+    xs, ys, xo, yo, dt = S.SECTORS[sector]
+    p = ob.default_params(max_disp=args.max_disp)
+    ctx = ob.Context(local)
+    if world > 1:
+        ids = [ob.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], rank, world)
+    own0, own1, in0, in1 = ob.band_plan(nx, ny, p, rank, world)
+    nav = ob.goes_nav(xs, ys, xo, yo)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+
+    # ---- synthetic inputs, resident in HBM (band rows [in0,in1) of the scene)
+    img1, img2 = S.make_pair_torch(nx, ny, args.seed, dev, limb_taper=taper, rows=(in0, in1))
+    nown = own1 - own0
+    u = torch.zeros((nown, nx), dtype=torch.float32, device=dev)
+    v = torch.zeros_like(u)
+    shorts = [torch.zeros((nown, nx), dtype=torch.int16, device=dev) for _ in range(4)]
+    torch.cuda.synchronize()
+
+    def step():
+        if world > 1:
+            ctx.oct_variational_optical_flow_band(img1, img2, u, v, nx, ny, p)
+            ctx.oct_pix2uv_band(nav, 0.0, dt, u, v, nx, own0, nown, *shorts, p)
+        else:
+            ctx.oct_variational_optical_flow(img1, img2, u, v, p)
+            ctx.oct_pix2uv_cuda(nav, 0.0, dt, u, v, *shorts, p)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    for _ in range(args.warmup):
+        step()
+    ctx.set_profile(True)          # per-launch events on the finest level's PCG kernels only
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_step = timed(step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    st = ctx.stats()               # of the last timed step
+    ctx.set_profile(False)
+    launches = int(st.kernel_launches)
+    mpix = nx * ny / 1e6
+
+    # ---- end to end through the host-buffer C-ABI entry point (N = 1) or its band equivalent
+    e2e = None
+    if not args.no_e2e:
+        if world == 1:
+            h1 = torch.empty((ny, nx), dtype=torch.float32, pin_memory=True); h1.copy_(img1)
+            h2 = torch.empty((ny, nx), dtype=torch.float32, pin_memory=True); h2.copy_(img2)
+            hu = torch.zeros((ny, nx), dtype=torch.float32, pin_memory=True)
+            hv = torch.zeros((ny, nx), dtype=torch.float32, pin_memory=True)
+            n1, n2 = h1.numpy(), h2.numpy()
+            hs = {k: torch.zeros((ny, nx), dtype=torch.int16, pin_memory=True).numpy()
+                  for k in ("uVal", "vVal", "uVal2", "vVal2")}
+
+            def e2e_step():
+                ctx.oct_optical_flow(n1, n2, nav, 0.0, dt, p, upix=hu.numpy(), vpix=hv.numpy(), out=hs)
+
+            h2d = 2 * nx * ny * 4
+            d2h = nx * ny * (2 * 4 + 4 * 2)
+        else:
+            h1 = torch.empty(img1.shape, dtype=torch.float32, pin_memory=True); h1.copy_(img1)
+            h2 = torch.empty(img2.shape, dtype=torch.float32, pin_memory=True); h2.copy_(img2)
+            hu = torch.zeros((nown, nx), dtype=torch.float32, pin_memory=True)
+            hv = torch.zeros_like(hu).pin_memory()
+            hs = [torch.zeros((nown, nx), dtype=torch.int16, pin_memory=True) for _ in range(4)]
+
+            def e2e_step():
+                with torch.cuda.stream(stream):
+                    img1.copy_(h1, non_blocking=True); img2.copy_(h2, non_blocking=True)
+                    ctx.oct_variational_optical_flow_band(img1, img2, u, v, nx, ny, p)
+                    ctx.oct_pix2uv_band(nav, 0.0, dt, u, v, nx, own0, nown, *shorts, p)
+                    hu.copy_(u, non_blocking=True); hv.copy_(v, non_blocking=True)
+                    for a, b in zip(hs, shorts):
+                        a.copy_(b, non_blocking=True)
+                ctx.synchronize()
+
+            h2d = 2 * nx * (in1 - in0) * 4
+            d2h = nx * nown * (2 * 4 + 4 * 2)
+        for _ in range(min(args.warmup, 1)):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+        e2e = {"value": mpix / (ms_e2e / 1e3), "unit": "Mpix/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "octane_optical_flow (host buffers, pinned)" if world == 1 else
+                      "pinned band H2D + octane_variational_flow_band_dev + octane_pix2uv_band_dev + D2H"}
+        del h1, h2
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (finest-level PCG passes, timed live above)
+    peak, peak_src = peaks()
+    k1 = B_PASS1 * st.finest_pixels / (st.finest_pass1_ms * 1e-3) / 1e9 if st.finest_pass1_ms > 0 else 0.0
+    k2 = B_PASS2 * st.finest_pixels / (st.finest_pass2_ms * 1e-3) / 1e9 if st.finest_pass2_ms > 0 else 0.0
+    dom = "pcg_pass2" if st.ms_pcg_pass2 >= st.ms_pcg_pass1 else "pcg_pass1"
+    ach = k2 if dom == "pcg_pass2" else k1
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get(dom)
+    except Exception:
+        pass
+    its = list(st.cg_iterations[:st.n_solves])
+    line = {
+        "metric": METRIC, "value": mpix / (ms_step / 1e3), "unit": "Mpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload} {nx}x{ny} band-2-like pair, {sector}", "nc": 1,
+                   "alpha": p.alpha, "lambda": p.lambda_, "kiters": p.kiters, "liters": p.liters, "cgiters": p.cgiters,
+                   "parallelism": f"row bands x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs and every level-3 plane are larger than L2 (no flush needed)" if nx * ny * 4 > 130e6
+                         else "working set of the coarse levels fits L2; inputs re-read from HBM each step"},
+        "clocks": clocks, "gpu_launches": launches * args.steps,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                     "bytes_per_pixel_per_launch": B_PASS2 if dom == "pcg_pass2" else B_PASS1,
+                     "pixels_per_launch": int(st.finest_pixels),
+                     "pass1": {"GB/s": k1, "avg_ms": st.finest_pass1_ms}, "pass2": {"GB/s": k2, "avg_ms": st.finest_pass2_ms},
+                     "whole_step": {"algorithmic_GB": st.algorithmic_bytes * world / 1e9,
+                                    "GB/s_per_gpu": st.algorithmic_bytes / (ms_step * 1e-3) / 1e9,
+                                    "frac": st.algorithmic_bytes / (ms_step * 1e-3) / 1e9 / peak}},
+        "stage_ms": {"pyramid": st.ms_pyramid, "build": st.ms_build, "pcg_pass1": st.ms_pcg_pass1,
+                     "pcg_pass2": st.ms_pcg_pass2, "update": st.ms_update, "nav": st.ms_nav,
+                     "note": "PCG passes timed at the finest level only"},
+        "cg_iterations": {"min": min(its), "max": max(its), "sum": sum(its)},
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = run_cpu_port(nx, ny, sector, args.seed)
+    if args.ref_cuda:
+        try:
+            line["ref_cuda_sm100"] = run_ref_cuda(nx, ny, sector, args.seed)
+        except Exception as e:
+            line["ref_cuda_sm100"] = {"unavailable": str(e)[:120]}
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

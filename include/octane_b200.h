@@ -114,6 +114,7 @@ int  octane_ctx_set_profile(octane_ctx* ctx, int on);      /* per-stage CUDA-eve
 int  octane_ctx_set_graphs(octane_ctx* ctx, int on);       /* CUDA-graph the PCG loop (default on) */
 int  octane_get_stats(octane_ctx* ctx, octane_stats* out);
 int  octane_ctx_synchronize(octane_ctx* ctx);
+void* octane_ctx_stream(octane_ctx* ctx);                  /* the cudaStream_t all work is ordered on */
 size_t octane_workspace_bytes(int nx, int ny, int nc, const octane_params* p);
 
 /* Pyramid geometry: level k has factor scaleF^(kiters-1-k) and size

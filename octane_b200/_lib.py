@@ -49,7 +49,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "octane_abi_version", "octane_last_error", "octane_device_count", "octane_params_default",
     "octane_ctx_create", "octane_ctx_destroy", "octane_ctx_set_profile", "octane_ctx_set_graphs",
-    "octane_get_stats", "octane_ctx_synchronize", "octane_workspace_bytes", "octane_level_dims",
+    "octane_get_stats", "octane_ctx_synchronize", "octane_ctx_stream", "octane_workspace_bytes", "octane_level_dims",
     "octane_variational_flow", "octane_pix2uv", "octane_optical_flow",
     "octane_variational_flow_dev", "octane_pix2uv_dev",
     "octane_stage_blur_decimate", "octane_stage_gradient", "octane_stage_zoom_in",
@@ -84,6 +84,8 @@ def load() -> C.CDLL:
     L.octane_ctx_set_graphs.argtypes = [vp, i]
     L.octane_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.octane_ctx_synchronize.argtypes = [vp]
+    L.octane_ctx_stream.argtypes = [vp]
+    L.octane_ctx_stream.restype = vp
     L.octane_workspace_bytes.argtypes = [i, i, i, PP]
     L.octane_workspace_bytes.restype = C.c_size_t
     L.octane_level_dims.argtypes = [i, i, PP, i, ip, ip]

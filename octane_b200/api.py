@@ -125,6 +125,11 @@ class Context:
     def synchronize(self):
         self._check(self._L.octane_ctx_synchronize(self._h))
 
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t (as int) that every call of this context is ordered on."""
+        return int(self._L.octane_ctx_stream(self._h) or 0)
+
     def stats(self) -> Stats:
         s = Stats()
         self._check(self._L.octane_get_stats(self._h, C.byref(s)))
@@ -180,14 +185,20 @@ class Context:
                                                           nrows, C.byref(p), _ptr(ur), _ptr(vr), _ptr(ur2), _ptr(vr2)))
 
     def oct_optical_flow(self, geo1, geo2, nav: Nav, t1: float, t2: float, p: Optional[Params] = None,
-                         cth=None, upix=None, vpix=None, nc: int = 1):
-        """Dispatcher (host arrays): returns dict(uPix, vPix, uVal, vVal, uVal2, vVal2, CTP, dT)."""
+                         cth=None, upix=None, vpix=None, nc: int = 1, out=None):
+        """Dispatcher (host arrays): returns dict(uPix, vPix, uVal, vVal, uVal2, vVal2, CTP, dT).
+        `out` may carry preallocated (e.g. pinned) int16 arrays under the same keys."""
         p = p or default_params()
         ny, nx = geo1.shape[-2:]
         upix = np.zeros((ny, nx), np.float32) if upix is None else upix
         vpix = np.zeros((ny, nx), np.float32) if vpix is None else vpix
-        out = {k: np.zeros((ny, nx), np.int16) for k in ("uVal", "vVal", "uVal2", "vVal2")}
-        ctp = np.zeros((ny, nx), np.int16) if p.doCTH else None
+        out = dict(out) if out else {}
+        for k in ("uVal", "vVal", "uVal2", "vVal2"):
+            if k not in out:
+                out[k] = np.zeros((ny, nx), np.int16)
+        ctp = out.get("CTP") if p.doCTH else None
+        if p.doCTH and ctp is None:
+            ctp = np.zeros((ny, nx), np.int16)
         dT = C.c_float()
         self._check(self._L.octane_optical_flow(self._h, _ptr(geo1), _ptr(geo2), _ptr(cth), nx, ny, nc, C.byref(nav),
                                                 t1, t2, C.byref(p), _ptr(upix), _ptr(vpix), _ptr(out["uVal"]),

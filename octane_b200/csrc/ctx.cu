@@ -737,6 +737,8 @@ int octane_ctx_synchronize(octane_ctx* c)
     return OCTANE_OK;
 }
 
+void* octane_ctx_stream(octane_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
 int octane_get_stats(octane_ctx* c, octane_stats* out)
 {
     if (!c || !out) return OCTANE_EINVAL;

@@ -13,6 +13,12 @@
 
 namespace octane {
 
+// The reference packs U_raw/V_raw (and U/V with -pd, and CTP) on the HOST:
+// (short)(float) on x86-64 is cvttss2si to int32 followed by truncation to 16 bits,
+// which wraps for |x| >= 32768 (e.g. the -9999 fill value times 100) where the GPU's
+// cvt.s16.f32 would saturate.  Reproduce the host behaviour.
+__device__ __forceinline__ short host_short(float x) { return (short)(int)x; }
+
 __device__ double oct_haversine(float lat1, float lon1, float lat2, float lon2, double rad, double rad2)
 {
     const double earthrad = 6371000.00;
@@ -137,11 +143,11 @@ k_pix2uv(NavParams nav, const float* __restrict__ u, const float* __restrict__ v
     for (size_t lxyz = (size_t)blockIdx.x * 256 + threadIdx.x; lxyz < n; lxyz += (size_t)gridDim.x * 256) {
         const int jj = (int)(lxyz / nx) + row0, ii = (int)(lxyz % nx);
         const float uf = u[lxyz], vf = v[lxyz];
-        ur2[lxyz] = (short)(100 * uf);                     // :335-336
-        vr2[lxyz] = (short)(100 * vf);
+        ur2[lxyz] = host_short(100 * uf);                  // :335-336
+        vr2[lxyz] = host_short(100 * vf);
         if (nav.pixuv) {                                   // :348-356
-            ur[lxyz] = (short)(100 * uf);
-            vr[lxyz] = (short)(100 * vf);
+            ur[lxyz] = host_short(100 * uf);
+            vr[lxyz] = host_short(100 * vf);
             continue;
         }
         double dans[2], xans[2];
@@ -164,7 +170,7 @@ k_pix2uv(NavParams nav, const float* __restrict__ u, const float* __restrict__ v
 __global__ void __launch_bounds__(256) k_ctp_pack(const float* __restrict__ cth, short* __restrict__ ctp, size_t n, int ir)
 {
     for (size_t k = (size_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (size_t)gridDim.x * 256)
-        ctp[k] = ir ? (short)((cth[k] - 300) * 100) : (short)cth[k];
+        ctp[k] = ir ? host_short((cth[k] - 300) * 100) : host_short(cth[k]);
 }
 
 void launch_pix2uv(const NavParams& np, const float* u, const float* v, int nx, int row0, int nrows,

@@ -43,9 +43,9 @@ k_blur_decimate(const float* __restrict__ src, Geom gs, float* __restrict__ dst,
     for (int t = tid; t < 2 * R + 1; t += TX * TY) gk[t] = GK[t];
     const int ii = blockIdx.x * TX + threadIdx.x;
     const int jj0 = ja + blockIdx.y * TY;
-    const int c = blockIdx.z;
-    src += (size_t)c * gs.plane;
-    dst += (size_t)c * gd.plane;
+    // Reference quirk kept for parity: zoom_out reads the blurred plane without a channel
+    // offset (:406), so every coarse-level channel is channel 0's blurred, decimated image.
+    dst += (size_t)blockIdx.z * gd.plane;
     const int i2 = (int)(ii / factor);                          // :369
     const int jj_last = min(jj0 + TY, jb) - 1;
     const int jsrc0 = (int)(jj0 / factor) - R;                  // first source row of the tile

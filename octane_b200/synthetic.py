@@ -73,11 +73,14 @@ SECTORS = {
 
 
 def make_pair_torch(nx: int, ny: int, seed: int, device, limb_taper: bool = False,
-                    drift=(0.8, -0.4), peak: float = 2.0, tile: int = 4096):
+                    drift=(0.8, -0.4), peak: float = 2.0, tile: int = 4096, rows=None, out=None):
     """Large-scene generator on `device` (torch): periodic `tile`^2 texture
     replicated over the scene with a slow brightness modulation, frame 2 =
     frame 1 sampled at (x-u, y-v) (bilinear on the periodic tile, exact
-    wrap-around).  Returns two ny x nx float32 CUDA tensors."""
+    wrap-around).  `rows=(r0, r1)` generates only that row band of the scene
+    (identical values to the same rows of the full scene), `out=(a, b)` writes
+    into existing (pinned host or device) tensors.  Returns two float32 tensors
+    of shape (r1-r0) x nx."""
     import torch
 
     t = min(tile, 1 << int(np.ceil(np.log2(max(nx, ny)))))
@@ -91,13 +94,17 @@ def make_pair_torch(nx: int, ny: int, seed: int, device, limb_taper: bool = Fals
         return ((1 - fy) * ((1 - fx) * base[y0, x0] + fx * base[y0, x1])
                 + fy * ((1 - fx) * base[y1, x0] + fx * base[y1, x1]))
 
-    img1 = torch.empty((ny, nx), dtype=torch.float32, device=device)
-    img2 = torch.empty((ny, nx), dtype=torch.float32, device=device)
+    r0, r1 = rows if rows is not None else (0, ny)
+    if out is not None:
+        img1, img2 = out
+    else:
+        img1 = torch.empty((r1 - r0, nx), dtype=torch.float32, device=device)
+        img2 = torch.empty((r1 - r0, nx), dtype=torch.float32, device=device)
     cx, cy, rad = 0.5 * (nx - 1), 0.5 * (ny - 1), nx / 4.0
     xs_full = torch.arange(nx, device=device, dtype=torch.float32)[None, :]
-    rows = max(1, (1 << 24) // nx)
-    for j0 in range(0, ny, rows):
-        j1 = min(ny, j0 + rows)
+    chunk = max(1, (1 << 24) // nx)
+    for j0 in range(r0, r1, chunk):
+        j1 = min(r1, j0 + chunk)
         ys = torch.arange(j0, j1, device=device, dtype=torch.float32)[:, None]
         xs = xs_full.expand(j1 - j0, nx)
         ysb = ys.expand(j1 - j0, nx)
@@ -115,6 +122,6 @@ def make_pair_torch(nx: int, ny: int, seed: int, device, limb_taper: bool = Fals
             r2 = (xs * xsc + xo) ** 2 + (ysb * ysc + yo) ** 2
             w = torch.clamp((0.0212 - r2) / (0.0212 - 0.021), 0.0, 1.0)
             a = a * w; b = b * w
-        img1[j0:j1] = a
-        img2[j0:j1] = b
+        img1[j0 - r0:j1 - r0].copy_(a)
+        img2[j0 - r0:j1 - r0].copy_(b)
     return img1, img2

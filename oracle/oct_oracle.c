@@ -162,7 +162,9 @@ void oracle_blur_decimate(const float *img, int nx, int ny, int nc, float factor
     int nxx, nyy;
     oracle_zoom_size(nx, ny, factor, &nxx, &nyy);
     for (int c = 0; c < nc; c++) {
-        blur_full(img + n * c, tmp, Is, GK, nx, ny, R);
+        /* Reference quirk: zoom_out samples `Is` without a channel offset (:406), so at
+         * every coarse level ALL channels are the blurred, decimated CHANNEL 0. */
+        if (c == 0) blur_full(img, tmp, Is, GK, nx, ny, R);
         float *o = out + (size_t)nxx * nyy * c;
 #pragma omp parallel for schedule(static)
         for (int jj = 0; jj < nyy; jj++)

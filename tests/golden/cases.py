@@ -1,0 +1,84 @@
+"""Seeded golden cases shared by make_golden.py (which runs the REFERENCE on a
+B200 to produce the fixtures) and by the parity tests (which replay the same
+inputs through the oracle and through the CUDA path)."""
+from __future__ import annotations
+
+import numpy as np
+
+from octane_b200 import synthetic as S
+
+# name: dict(nx, ny, seed, kind, drift, nc, params overrides, first guess)
+VARIATIONAL = {
+    "var_96x80_shift": dict(nx=96, ny=80, seed=11, kind="shift", drift=(1.5, -0.75)),
+    "var_200x160_vortex": dict(nx=200, ny=160, seed=12, kind="vortex"),
+    "var_63x70_k3": dict(nx=63, ny=70, seed=13, kind="vortex", params=dict(kiters=3)),
+    "var_128x96_nc2": dict(nx=128, ny=96, seed=14, kind="vortex", nc=2),
+    "var_160x120_fg": dict(nx=160, ny=120, seed=15, kind="vortex", first_guess=True, params=dict(lambdac=0.5)),
+    "var_150x130_brox": dict(nx=150, ny=130, seed=16, kind="vortex",
+                             params=dict(dozim=0, alpha=10.0, lambda_=2.0, kiters=3, liters=2)),
+    "var_101x67_cg5": dict(nx=101, ny=67, seed=17, kind="shift", drift=(-0.6, 0.9), params=dict(cgiters=5, kiters=2)),
+}
+
+NAVIGATION = {
+    # GOES fixed grid, mesoscale sector away from the limb
+    "nav_goes_meso": dict(kind="goes", sector="meso_0.5km", nx=120, ny=90, minX=0, minY=0),
+    # full-disk corner: off-earth pixels (d<0) and the limb cut x^2+y^2 > 0.021
+    "nav_goes_limb": dict(kind="goes", sector="fulldisk_0.5km", nx=160, ny=120, minX=2900, minY=2900),
+    "nav_goes_2km_offset": dict(kind="goes", sector="meso_2km", nx=100, ny=100, minX=1500, minY=700),
+    "nav_polar": dict(kind="polar", nx=90, ny=110),
+    "nav_polar_pole": dict(kind="polar", nx=64, ny=64, lat1=90.0),
+    "nav_merc": dict(kind="merc", nx=110, ny=70),
+    "nav_pixuv": dict(kind="goes", sector="meso_0.5km", nx=80, ny=60, minX=0, minY=0, pixuv=1),
+    "nav_moved": dict(kind="goes", sector="meso_0.5km", nx=80, ny=60, minX=0, minY=0, moved=True),
+}
+
+
+def variational_inputs(c):
+    nx, ny, nc = c["nx"], c["ny"], c.get("nc", 1)
+    i1s, i2s = [], []
+    u = v = None
+    for ch in range(nc):
+        a, b, u, v = S.make_pair(nx, ny, c["seed"] + 100 * ch, kind=c["kind"], drift=c.get("drift", (0.8, -0.4)))
+        i1s.append(a); i2s.append(b)
+    img1 = np.ascontiguousarray(np.stack(i1s)) if nc > 1 else i1s[0]
+    img2 = np.ascontiguousarray(np.stack(i2s)) if nc > 1 else i2s[0]
+    u0 = v0 = None
+    if c.get("first_guess"):
+        y, x = np.mgrid[0:ny, 0:nx].astype(np.float32)
+        u0 = (0.6 + 0.3 * np.sin(x / 23.0) * np.cos(y / 31.0)).astype(np.float32)
+        v0 = (-0.3 + 0.2 * np.cos(x / 19.0 + y / 29.0)).astype(np.float32)
+    return img1, img2, u0, v0
+
+
+def nav_flow(nx, ny, seed=5):
+    """A smooth displacement field with a few special values (zero, exact integers, -9999 fill)."""
+    y, x = np.mgrid[0:ny, 0:nx].astype(np.float32)
+    u = (1.7 * np.sin(x / 17.0) + 0.9 * np.cos(y / 13.0) + 0.4).astype(np.float32)
+    v = (-1.1 * np.cos(x / 11.0) * np.sin(y / 19.0) - 0.25).astype(np.float32)
+    u[0, 0] = 0.0; v[0, 0] = 0.0
+    u[1, 1] = 2.0; v[1, 1] = -3.0
+    u[2, 2] = -9999.0; v[2, 2] = -9999.0
+    return u, v
+
+
+def nav_constants(c):
+    """kwargs for goes_nav() + (t1, t2) + flag dict."""
+    kind = c["kind"]
+    if kind == "goes":
+        xs, ys, xo, yo, dt = S.SECTORS[c["sector"]]
+        kw = dict(xScale=xs, yScale=ys, xOffset=xo, yOffset=yo, minX=c.get("minX", 0), minY=c.get("minY", 0))
+        if c.get("moved"):
+            kw.update(g2xOffset=xo + 0.001, g2yOffset=yo)
+        extra = {}
+    elif kind == "polar":
+        # orthographic polar grid in metres (1 km pixels), centred near the pole
+        kw = dict(xScale=1000.0, yScale=-1000.0, xOffset=-45000.0, yOffset=55000.0)
+        extra = dict(lat1=c.get("lat1", 75.0), lon0=-150.0, R=6371228.0)
+        dt = 3600.0
+    else:
+        # spherical Mercator in metres (2 km pixels)
+        kw = dict(xScale=2000.0, yScale=-2000.0, xOffset=-110000.0, yOffset=4100000.0)
+        extra = dict(lon1=float(np.deg2rad(-95.0)), R=6371228.0)
+        dt = 3600.0
+    flags = dict(pixuv=c.get("pixuv", 0), dopolar=int(kind == "polar"), domerc=int(kind == "merc"))
+    return kw, extra, 1000.0, 1000.0 + dt, flags

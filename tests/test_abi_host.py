@@ -1,0 +1,158 @@
+"""CPU tests of the boundary and the host logic (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import octane_b200 as ob
+from octane_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "octane_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(octane_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.load()
+    names = header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/octane_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names, "python binding list and header disagree"
+    assert L.octane_abi_version() == 1
+
+
+def test_no_torch_types_in_abi():
+    src = open(os.path.join(ROOT, "include", "octane_b200.h")).read()
+    assert "torch" not in src.replace("no C++ / torch types", "") and "std::" not in src and "extern \"C\"" in src
+
+
+def test_struct_layout_matches_header():
+    # sizes computed by the C compiler vs ctypes
+    code = r'''
+#include <stdio.h>
+#include "octane_b200.h"
+int main(){printf("%zu %zu %zu\n", sizeof(octane_params), sizeof(octane_nav), sizeof(octane_stats));return 0;}
+'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(code)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        a, b, c = map(int, subprocess.check_output([os.path.join(d, "t")]).split())
+    assert (a, b, c) == (C.sizeof(ob.Params), C.sizeof(ob.Nav), C.sizeof(ob.Stats))
+
+
+def test_defaults_are_the_reference_defaults():
+    p = ob.default_params()      # src/main.cc:77-98
+    assert (p.alpha, p.lambda_, p.lambdac, p.scaleF) == (5.0, 1.0, 0.0, 0.5)
+    assert (p.kiters, p.liters, p.cgiters, p.dozim) == (4, 3, 30, 1)
+    assert (p.pixuv, p.dopolar, p.domerc, p.setdevice) == (0, 0, 0, 0)
+
+
+def test_level_dims_bit_exact(oracle):
+    for nx, ny in [(500, 500), (2000, 2000), (10000, 6000), (21696, 21696), (63, 70), (1001, 333), (4097, 257)]:
+        for k in (1, 2, 3, 4, 5):
+            p = ob.default_params(kiters=k)
+            if min(nx, ny) * 0.5 ** (k - 1) < 4:
+                continue
+            assert ob.level_dims(nx, ny, p) == oracle.level_dims(nx, ny, kiters=k)
+    assert ob.level_dims(21696, 21696) == [(2712, 2712), (5424, 5424), (10848, 10848), (21696, 21696)]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ob.OctaneError) as e:
+        ob.Context(0)
+    assert e.value.code == -1          # ENODEV: the product path fails loudly without CUDA
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "octane_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cc", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower().replace("no python or cpu fallback", ""), f"{f} mentions the oracle"
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+@pytest.mark.parametrize("shape", [(21696, 21696), (10000, 6000), (2000, 2000)])
+def test_band_plan_tiles_the_scene(shape, world):
+    nx, ny = shape
+    p = ob.default_params()
+    prev = 0
+    for r in range(world):
+        own0, own1, in0, in1 = ob.band_plan(nx, ny, p, r, world)
+        assert own0 == prev and own1 > own0
+        assert 0 <= in0 <= own0 and own1 <= in1 <= ny
+        if world > 1:
+            # blur radius 5 at full res for the coarsest level's halo: (max_disp/8 + 3 + 4 rows) * 8 + 5
+            if r > 0:
+                assert own0 - in0 >= p.max_disp + 5
+            if r < world - 1:
+                assert in1 - own1 >= p.max_disp + 5
+        else:
+            assert (in0, in1) == (0, ny)
+        prev = own1
+    assert prev == ny
+
+
+def test_band_plan_rejects_thin_bands():
+    with pytest.raises(ob.OctaneError):
+        ob.band_plan(256, 128, ob.default_params(), 0, 8)     # coarsest level: 16 rows / 8 ranks
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # bootstrap pattern of bench.py: rank 0 makes the 128-byte id, everyone receives it
+        ids = [bytes(range(128)) if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nx, ny = 640, 512
+        p = ob.default_params(max_disp=8)
+        own0, own1, in0, in1 = ob.band_plan(nx, ny, p, rank, world)
+        # each rank "solves" its band: here the band is filled with its global row index
+        import torch
+        band = torch.arange(own0, own1, dtype=torch.float32)[:, None].expand(own1 - own0, nx).contiguous()
+        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([own1 - own0]))
+        parts = [torch.zeros((int(s.item()), nx)) for s in sizes]
+        # uneven bands: gather through object lists
+        objs = [None] * world
+        dist.all_gather_object(objs, band.numpy())
+        full = np.concatenate(objs, axis=0)
+        ok = full.shape == (ny, nx) and np.array_equal(full[:, 0], np.arange(ny, dtype=np.float32))
+        # time reduction used by bench.py: max over ranks
+        t = torch.tensor([float(rank + 1)])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        q.put((rank, ids[0] == bytes(range(128)), ok, float(t.item()), (own0, own1, in0, in1)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_band_bootstrap_and_gather():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for pr in procs:
+        pr.join(timeout=60)
+    assert all(r[1] and r[2] for r in res)
+    assert all(r[3] == 2.0 for r in res)
+    assert res[0][4][1] == res[1][4][0] == 256           # bands meet at the middle row
+    assert res[0][4][3] > 256 and res[1][4][2] < 256     # and overlap in their inputs

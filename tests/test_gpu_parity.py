@@ -1,0 +1,292 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against
+(1) fixtures produced by the reference itself (tests/golden), (2) the CPU
+oracle on the same seeded inputs, (3) size-independent properties at the
+BASELINE.json sizes.
+
+Tolerances (BASELINE.json north_star): pyramid dimensions and indexing
+bit-exact; fp32 flow mean |du,dv| <= 1e-3 px, max <= 1e-2 px; navigated speed
+within 0.01 m/s (= 1 count of the short outputs)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import octane_b200 as ob
+from conftest import load_golden
+from octane_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+MEAN_TOL, MAX_TOL = 1e-3, 1e-2
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def solve(ctx, c, img1, img2, u0, v0):
+    ny, nx = img1.shape[-2:]
+    p = ob.default_params(first_guess=int(u0 is not None), **c.get("params", {}))
+    u = np.zeros((ny, nx), np.float32) if u0 is None else u0.copy()
+    v = np.zeros((ny, nx), np.float32) if v0 is None else v0.copy()
+    ctx.oct_variational_optical_flow(img1, img2, u, v, p, nc=c.get("nc", 1))
+    return u, v, p
+
+
+@pytest.mark.parametrize("name", sorted(cases.VARIATIONAL))
+def test_flow_matches_reference_fixture(ctx, name):
+    c = cases.VARIATIONAL[name]
+    g = load_golden(name)
+    img1, img2, u0, v0 = cases.variational_inputs(c)
+    u, v, _ = solve(ctx, c, img1, img2, u0, v0)
+    du, dv = np.abs(u - g["u"]), np.abs(v - g["v"])
+    assert du.mean() < MEAN_TOL and dv.mean() < MEAN_TOL
+    assert du.max() < MAX_TOL and dv.max() < MAX_TOL
+    assert max(du.max(), dv.max()) < max(20 * float(g["spread"].max()), 2e-4)
+
+
+@pytest.mark.parametrize("name", sorted(cases.VARIATIONAL))
+def test_flow_matches_oracle(ctx, oracle, name):
+    c = cases.VARIATIONAL[name]
+    img1, img2, u0, v0 = cases.variational_inputs(c)
+    u, v, p = solve(ctx, c, img1, img2, u0, v0)
+    st = ctx.stats()
+    uo, vo, its = oracle.variational_flow(img1, img2, oracle.params(**c.get("params", {})), u0, v0, nc=c.get("nc", 1))
+    assert np.abs(u - uo).mean() < 1e-4 and np.abs(v - vo).mean() < 1e-4
+    assert np.abs(u - uo).max() < 2e-3 and np.abs(v - vo).max() < 2e-3
+    assert list(st.cg_iterations[:st.n_solves]) == list(its)
+    assert st.kernel_launches > 0
+    dims = [(st.level_nx[k], st.level_ny[k]) for k in range(st.n_levels)]
+    assert dims == oracle.level_dims(c["nx"], c["ny"], kiters=p.kiters)       # bit-exact pyramid geometry
+
+
+@pytest.mark.parametrize("name", sorted(cases.NAVIGATION))
+def test_navigation_matches_reference_fixture(ctx, name):
+    c = cases.NAVIGATION[name]
+    g = load_golden(name)
+    kw, extra, t1, t2, flags = cases.nav_constants(c)
+    nav = ob.goes_nav(**kw)
+    for k, val in extra.items():
+        setattr(nav, k, val)
+    p = ob.default_params(**flags)
+    ny, nx = g["u"].shape
+    outs = [np.full((ny, nx), 7, np.int16) for _ in range(4)]
+    dT, moved = ctx.oct_pix2uv_cuda(nav, t1, t2, g["u"], g["v"], *outs, p)
+    assert moved == bool(c.get("moved")) and abs(dT - float(g["dT"])) < 1e-6
+    U, V, U2, V2 = outs
+    # same CUDA libm, same expression order: identical shorts
+    assert np.array_equal(U, g["U"]) and np.array_equal(V, g["V"])
+    if not flags["pixuv"]:
+        assert np.array_equal(U2, g["U_raw"]) and np.array_equal(V2, g["V_raw"])
+    else:   # documented deviation: the reference leaves U_raw/V_raw unwritten with -pd; we write 100*u
+        assert np.array_equal(U2, U) and np.array_equal(V2, V)
+
+
+@pytest.mark.parametrize("ir", [0, 1])
+def test_dispatcher_with_cloud_top_heights(ctx, ir):
+    g = load_golden(f"dispatch_cth_ir{ir}")
+    kw, extra, t1, t2, flags = cases.nav_constants(cases.NAVIGATION["nav_goes_meso"])
+    p = ob.default_params(doCTH=1, ir=ir)
+    out = ctx.oct_optical_flow(g["img1"], g["img2"], ob.goes_nav(**kw), t1, t2, p, cth=g["cth"])
+    assert np.abs(out["uPix"] - g["uPix"]).max() < 2e-4 and np.abs(out["vPix"] - g["vPix"]).max() < 2e-4
+    assert np.array_equal(out["CTP"], g["CTP"])
+    for a, b in (("uVal", "U"), ("vVal", "V"), ("uVal2", "U_raw"), ("vVal2", "V_raw")):
+        assert np.abs(out[a].astype(int) - g[b]).max() <= 1
+    assert abs(out["dT"] - float(g["dT"])) < 1e-6
+
+
+# ---- stage-level parity against the oracle --------------------------------------------
+@pytest.mark.parametrize("shape", [(96, 80), (257, 131), (500, 500)])
+@pytest.mark.parametrize("factor", [0.5, 0.25, 0.125])
+def test_stage_blur_decimate(ctx, oracle, shape, factor):
+    import torch
+    nx, ny = shape
+    img = S.texture(nx, ny, 21)
+    nxx, nyy = int(nx * factor + 0.5), int(ny * factor + 0.5)
+    want = np.zeros((nyy, nxx), np.float32)
+    oracle.lib().oracle_blur_decimate(img, nx, ny, 1, factor, want)
+    got = torch.zeros((nyy, nxx), device="cuda")
+    ctx.stage_blur_decimate(dev(img), nx, ny, 1, factor, got)
+    got = got.cpu().numpy()
+    assert got.shape == want.shape                                # dims bit-exact
+    # taps come from CUDA expf vs glibc expf (<= 1 ulp): values to 1e-6 relative
+    assert np.abs(got - want).max() <= 1e-6 * 255 * 4
+
+
+@pytest.mark.parametrize("shape", [(96, 80), (257, 131), (33, 17)])
+def test_stage_gradient_bit_exact(ctx, oracle, shape):
+    import torch
+    nx, ny = shape
+    img = S.texture(nx, ny, 22)
+    gx, gy = np.zeros_like(img), np.zeros_like(img)
+    oracle.lib().oracle_gradient(img, gx, gy, nx, ny, 1)
+    dgx, dgy = torch.zeros((ny, nx), device="cuda"), torch.zeros((ny, nx), device="cuda")
+    ctx.stage_gradient(dev(img), nx, ny, 1, dgx, dgy)
+    assert np.array_equal(dgx.cpu().numpy(), gx) and np.array_equal(dgy.cpu().numpy(), gy)
+
+
+@pytest.mark.parametrize("dims", [((63, 63), (125, 125)), ((125, 125), (250, 250)), ((16, 18), (32, 35)), ((40, 30), (81, 59))])
+def test_stage_zoom_in_bit_exact(ctx, oracle, dims):
+    import torch
+    (nx, ny), (nxx, nyy) = dims
+    u, _ = S.flow_field(nx, ny)
+    u = u.astype(np.float32)
+    want = np.zeros((nyy, nxx), np.float32)
+    oracle.lib().oracle_zoom_in(u, want, nx, ny, nxx, nyy, 0.5)
+    got = torch.zeros((nyy, nxx), device="cuda")
+    ctx.stage_zoom_in(dev(u), nx, ny, nxx, nyy, 0.5, got)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("gnc", [0, 1, 2])
+@pytest.mark.parametrize("nc", [1, 2])
+def test_stage_build_and_pcg(ctx, oracle, gnc, nc):
+    import torch
+    nx, ny = 150, 110
+    chans1, chans2 = [], []
+    for ch in range(nc):
+        a, b, ut, vt = S.make_pair(nx, ny, 30 + ch)
+        chans1.append(a); chans2.append(b)
+    g1 = np.ascontiguousarray(np.stack(chans1)); g2 = np.ascontiguousarray(np.stack(chans2))
+    u = (0.7 * ut).astype(np.float32); v = (0.7 * vt).astype(np.float32)
+    uh = (0.5 * ut).astype(np.float32); vh = (0.5 * vt).astype(np.float32)
+    p = ob.default_params()
+    lambdac = 0.25
+    # oracle: gradients then build
+    L = oracle.lib()
+    n = nx * ny
+    f = {k: np.zeros((nc, ny, nx), np.float32) for k in ("g1x", "g1y", "g2x", "g2y", "g2xx", "g2xy", "g2yy")}
+    L.oracle_gradient(g1, f["g1x"], f["g1y"], nx, ny, nc)
+    L.oracle_gradient(g2, f["g2x"], f["g2y"], nx, ny, nc)
+    L.oracle_gradient(f["g2x"], f["g2xx"], f["g2xy"], nx, ny, nc)
+    L.oracle_gradient(f["g2y"], f["g2xy"], f["g2yy"], nx, ny, nc)
+    coef = np.zeros((7, ny, nx), np.float32); bu = np.zeros((ny, nx), np.float32); bv = np.zeros((ny, nx), np.float32)
+    L.oracle_build(u, v, uh.ctypes.data, vh.ctypes.data, g1, f["g1x"], f["g1y"], g2, f["g2x"], f["g2y"], f["g2xx"],
+                   f["g2xy"], f["g2yy"], nx, ny, nc, p.alpha, p.lambda_ / p.alpha, lambdac, gnc, 1, coef, bu, bv)
+    dcoef = torch.zeros((7, ny, nx), device="cuda"); dbu = torch.zeros((ny, nx), device="cuda"); dbv = torch.zeros((ny, nx), device="cuda")
+    ctx.stage_build(dev(u), dev(v), dev(uh), dev(vh), dev(g1), dev(g2), nx, ny, nc, p, lambdac, gnc, dcoef, dbu, dbv)
+    gc, gbu, gbv = dcoef.cpu().numpy(), dbu.cpu().numpy(), dbv.cpu().numpy()
+    scale = np.abs(coef).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(gc - coef) / scale).max() < 2e-5          # FMA contraction differences only
+    assert np.abs(gbu - bu).max() < 2e-5 * max(1.0, np.abs(bu).max()) and np.abs(gbv - bv).max() < 2e-5 * max(1.0, np.abs(bv).max())
+    # boundary-merged entries: absent neighbours are exactly zero
+    assert np.all(gc[3][:, 0] == 0) and np.all(gc[5][:, -1] == 0) and np.all(gc[4][0, :] == 0) and np.all(gc[6][-1, :] == 0)
+    # PCG on the oracle's system: same iterate after the same number of iterations
+    for iters in (1, 7, 30):
+        b1, b2 = bu.copy(), bv.copy()
+        xu, xv = np.zeros((ny, nx), np.float32), np.zeros((ny, nx), np.float32)
+        work = np.zeros(8 * n, np.float32)
+        its = L.oracle_pcg(coef, b1, b2, xu, xv, nx, ny, iters, 1e-8, work)
+        dxu, dxv = torch.zeros((ny, nx), device="cuda"), torch.zeros((ny, nx), device="cuda")
+        got_its = ctx.stage_pcg(dev(coef), dev(bu), dev(bv), nx, ny, iters, 1e-8, dxu, dxv)
+        assert got_its == its
+        tol = 5e-5 * max(1.0, np.abs(xu).max())
+        assert np.abs(dxu.cpu().numpy() - xu).max() < tol and np.abs(dxv.cpu().numpy() - xv).max() < tol
+
+
+def test_pcg_stop_rule_and_zero_rhs(ctx):
+    import torch
+    nx, ny = 64, 48
+    coef = np.zeros((7, ny, nx), np.float32)
+    coef[0] = 9; coef[2] = 9
+    for k in (3, 4, 5, 6):
+        coef[k] = -1
+    coef[3][:, 0] = 0; coef[5][:, -1] = 0; coef[4][0, :] = 0; coef[6][-1, :] = 0
+    z = np.zeros((ny, nx), np.float32)
+    dxu, dxv = torch.ones((ny, nx), device="cuda"), torch.ones((ny, nx), device="cuda")
+    assert ctx.stage_pcg(dev(coef), dev(z), dev(z), nx, ny, 30, 1e-8, dxu, dxv) == 0     # ||b||^2 <= tol: no iteration
+    assert float(dxu.abs().max()) == 0 and float(dxv.abs().max()) == 0
+    b = np.random.default_rng(1).standard_normal((ny, nx)).astype(np.float32)
+    its = ctx.stage_pcg(dev(coef), dev(b), dev(b), nx, ny, 200, 1e-8, dxu, dxv)
+    assert 0 < its < 200                                                               # converges before the cap
+
+
+# ---- size-independent properties at the BASELINE sizes ----------------------------------
+def test_meso_2000_matches_oracle(ctx, oracle):
+    nx = ny = 2000
+    import torch
+    a, b = S.make_pair_torch(nx, ny, 2, "cuda")
+    i1, i2 = a.cpu().numpy(), b.cpu().numpy()
+    u, v = np.zeros((ny, nx), np.float32), np.zeros((ny, nx), np.float32)
+    ctx.oct_variational_optical_flow(i1, i2, u, v, ob.default_params())
+    uo, vo, its = oracle.variational_flow(i1, i2)
+    assert np.abs(u - uo).mean() < MEAN_TOL and np.abs(v - vo).mean() < MEAN_TOL
+    assert np.abs(u - uo).max() < MAX_TOL and np.abs(v - vo).max() < MAX_TOL
+    st = ctx.stats()
+    assert list(st.cg_iterations[:st.n_solves]) == list(its)
+
+
+@pytest.mark.parametrize("workload", ["conus", "fulldisk"])
+def test_large_scene_properties(ctx, workload):
+    """CONUS 10000x6000 and full disk 21696x21696 (beyond the reference's int CSR limit):
+    bit-exact pyramid dims, run-to-run bit-reproducibility, recovery of the known
+    displacement, navigation round trip of the recovered flow."""
+    import torch
+    nx, ny, sector, taper = {"conus": (10000, 6000, "conus_0.5km", False),
+                             "fulldisk": (21696, 21696, "fulldisk_0.5km", True)}[workload]
+    a, b = S.make_pair_torch(nx, ny, 4, "cuda", limb_taper=taper)
+    u = torch.zeros((ny, nx), device="cuda"); v = torch.zeros_like(u)
+    p = ob.default_params()
+    ctx.oct_variational_optical_flow(a, b, u, v, p)
+    ctx.synchronize()
+    st = ctx.stats()
+    dims = [(st.level_nx[k], st.level_ny[k]) for k in range(st.n_levels)]
+    assert dims == [(int(nx * f + 0.5), int(ny * f + 0.5)) for f in (0.125, 0.25, 0.5, 1.0)]
+    assert all(0 < i <= 30 for i in st.cg_iterations[:st.n_solves])
+    assert bool(torch.isfinite(u).all()) and bool(torch.isfinite(v).all())
+    # known flow: drift (0.8,-0.4) + vortex of peak 2 px; compare on a central window away from the limb
+    ys, xs = slice(ny // 2 - 1500, ny // 2 + 1500), slice(nx // 2 - 1500, nx // 2 + 1500)
+    ut, vt = S.flow_field(nx, ny)
+    eu = (u[ys, xs].cpu().numpy() - ut[ys, xs]); ev = (v[ys, xs].cpu().numpy() - vt[ys, xs])
+    assert np.abs(eu).mean() < 0.05 and np.abs(ev).mean() < 0.05
+    # determinism: fixed-order reductions make a second run bit-identical
+    u2 = torch.zeros_like(u); v2 = torch.zeros_like(v)
+    ctx.oct_variational_optical_flow(a, b, u2, v2, p)
+    ctx.synchronize()
+    assert torch.equal(u, u2) and torch.equal(v, v2)
+    # navigation of the whole scene: U_raw is exactly (short)(100*u), fill/limb pixels are 0
+    xsc, ysc, xo, yo, dt = S.SECTORS[sector]
+    outs = [torch.zeros((ny, nx), dtype=torch.int16, device="cuda") for _ in range(4)]
+    ctx.oct_pix2uv_cuda(ob.goes_nav(xsc, ysc, xo, yo), 0.0, dt, u, v, *outs, p)
+    ctx.synchronize()
+    assert torch.equal(outs[2], (100 * u).to(torch.int32).to(torch.int16))
+    if taper:
+        assert int(outs[0][0, 0]) == 0 and int(outs[1][0, 0]) == 0          # off-earth corner
+    # speed = displacement * ~500 m / dt: centre pixel within 5 %
+    cy, cx = ny // 2, nx // 2
+    ms = float(outs[0][cy, cx]) / 100.0
+    px = float(u[cy, cx])
+    gsd = 35786023.0 * 1.4e-5
+    if abs(px) > 0.2:
+        assert abs(ms - px * gsd / dt) < 0.08 * abs(px * gsd / dt) + 0.02
+
+
+def test_errors_are_codes_not_exits(ctx):
+    img = np.zeros((8, 8), np.float32)
+    u = np.zeros((8, 8), np.float32)
+    with pytest.raises(ob.OctaneError) as e:       # level smaller than 4 pixels
+        ctx.oct_variational_optical_flow(img, img, u, u.copy(), ob.default_params())
+    assert e.value.code == -2
+    with pytest.raises(ob.OctaneError):
+        ctx.oct_variational_optical_flow(img, img, u, u.copy(), ob.default_params(kiters=1, alpha=0.0))
+    c2 = ob.Context(99)          # out-of-range device -> device 0, as the reference (:1260-1264)
+    c2.close()
+
+
+def test_graph_and_plain_launch_paths_agree(ctx):
+    i1, i2, _, _ = S.make_pair(300, 220, 40)
+    p = ob.default_params()
+    u1, v1 = np.zeros((220, 300), np.float32), np.zeros((220, 300), np.float32)
+    ctx.oct_variational_optical_flow(i1, i2, u1, v1, p)
+    ctx.set_graphs(False)
+    u2, v2 = np.zeros_like(u1), np.zeros_like(v1)
+    ctx.oct_variational_optical_flow(i1, i2, u2, v2, p)
+    ctx.set_graphs(True)
+    ctx.set_profile(True)
+    u3, v3 = np.zeros_like(u1), np.zeros_like(v1)
+    ctx.oct_variational_optical_flow(i1, i2, u3, v3, p)
+    st = ctx.stats()
+    ctx.set_profile(False)
+    assert np.array_equal(u1, u2) and np.array_equal(v1, v2) and np.array_equal(u1, u3)
+    assert st.finest_pass1_ms > 0 and st.finest_pass2_ms > 0 and st.n_pcg_pass1 == st.n_pcg_pass2 > 0
