@@ -157,6 +157,7 @@ struct octane_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool profile = false, graphs = true;
+    bool use_tma = getenv("OCTANE_NO_TMA") == nullptr;   // developer switch: v1 pass-1 kernel everywhere
     Comm comm;
     // workspace
     char* arena = nullptr;
@@ -352,7 +353,10 @@ int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve)
     for (int ki = 0; ki < iters; ki++) {
         {
             Scope s(c, CAT_P1, level, solve, ki);
-            launch_pcg_pass1(b, L.g, L.own0, L.own1, ki == 0, cur, multi, c->sm_count, c->stream);
+            if (c->use_tma && pcg_pass1_tma_usable(L.g, L.own1 - L.own0))
+                launch_pcg_pass1_tma(b, L.g, L.own0, L.own1, ki == 0, cur, multi, c->sm_count, c->stream);
+            else
+                launch_pcg_pass1(b, L.g, L.own0, L.own1, ki == 0, cur, multi, c->sm_count, c->stream);
             c->launches++;
         }
         if (multi) {

@@ -52,6 +52,10 @@ int build_partial_blocks(const Geom& g, int nrows);
 // the ping-pong p buffers holds p_old.
 void launch_pcg_pass1(const PcgBuffers& b, const Geom& g, int ja, int jb, int first, int cur, int store_halo,
                       int sm_count, cudaStream_t st);
+// large levels: persistent TMA-fed variant of pass 1 (pcg_tma.cu)
+bool pcg_pass1_tma_usable(const Geom& g, int nrows);
+void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, int first, int cur, int store_halo,
+                          int sm_count, cudaStream_t st);
 void launch_pcg_pass2(const PcgBuffers& b, const Geom& g, int ja, int jb, int first, int cur, int sm_count,
                       cudaStream_t st);
 void launch_update_uv(float* u, float* v, const float* xu, const float* xv, const Geom& g, int ja, int jb,
