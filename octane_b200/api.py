@@ -148,23 +148,46 @@ class Context:
             raise OctaneError(rc, L.octane_last_error().decode())
         return buf.raw
 
+    # ---- stream ordering with the host framework (device-pointer entry points only)
+    def _ext_stream(self):
+        import torch
+        if getattr(self, "_ext", None) is None:
+            self._ext = torch.cuda.ExternalStream(self.stream_ptr, device=torch.device("cuda", self.device))
+        return self._ext
+
+    def _after_torch(self):
+        """our stream waits for work already queued on torch's current stream (tensor producers)"""
+        import torch
+        self._ext_stream().wait_stream(torch.cuda.current_stream(self.device))
+
+    def _before_torch(self):
+        """torch's current stream waits for our stream (tensor consumers)"""
+        import torch
+        torch.cuda.current_stream(self.device).wait_stream(self._ext_stream())
+
     # ---- the reference's operators
     def oct_variational_optical_flow(self, geo1, geo2, u, v, p: Optional[Params] = None, nc: int = 1):
         """u, v in/out (ny x nx float32).  numpy -> host entry point; torch CUDA -> device entry point."""
         p = p or default_params()
         ny, nx = geo1.shape[-2:]
-        if _is_torch(geo1):
+        dev = _is_torch(geo1)
+        if dev:
             fn = self._L.octane_variational_flow_dev
+            self._after_torch()
         else:
             fn = self._L.octane_variational_flow
             for a in (geo1, geo2, u, v):
                 assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
         self._check(fn(self._h, _ptr(geo1), _ptr(geo2), nx, ny, nc, C.byref(p), _ptr(u), _ptr(v)))
+        if dev:
+            self._before_torch()
         return u, v
 
     def oct_variational_optical_flow_band(self, geo1_band, geo2_band, u_band, v_band, nx, ny, p: Params, nc: int = 1):
+        self._after_torch()
         self._check(self._L.octane_variational_flow_band_dev(self._h, _ptr(geo1_band), _ptr(geo2_band), nx, ny, nc,
                                                              C.byref(p), _ptr(u_band), _ptr(v_band)))
+        self._before_torch()
         return u_band, v_band
 
     def oct_pix2uv_cuda(self, nav: Nav, t1: float, t2: float, u, v, ur, vr, ur2, vr2, p: Optional[Params] = None):
@@ -172,8 +195,10 @@ class Context:
         p = p or default_params()
         ny, nx = u.shape
         if _is_torch(u):
+            self._after_torch()
             rc = self._check(self._L.octane_pix2uv_dev(self._h, C.byref(nav), t1, t2, _ptr(u), _ptr(v), nx, ny,
                                                        C.byref(p), _ptr(ur), _ptr(vr), _ptr(ur2), _ptr(vr2)))
+            self._before_torch()
             return float(np.float32(t2 - t1)), rc == 1
         dT = C.c_float()
         rc = self._check(self._L.octane_pix2uv(self._h, C.byref(nav), t1, t2, _ptr(u), _ptr(v), nx, ny, C.byref(p),
@@ -181,8 +206,11 @@ class Context:
         return dT.value, rc == 1
 
     def oct_pix2uv_band(self, nav: Nav, t1, t2, u, v, nx, row0, nrows, ur, vr, ur2, vr2, p: Params):
-        return self._check(self._L.octane_pix2uv_band_dev(self._h, C.byref(nav), t1, t2, _ptr(u), _ptr(v), nx, row0,
-                                                          nrows, C.byref(p), _ptr(ur), _ptr(vr), _ptr(ur2), _ptr(vr2)))
+        self._after_torch()
+        rc = self._check(self._L.octane_pix2uv_band_dev(self._h, C.byref(nav), t1, t2, _ptr(u), _ptr(v), nx, row0,
+                                                        nrows, C.byref(p), _ptr(ur), _ptr(vr), _ptr(ur2), _ptr(vr2)))
+        self._before_torch()
+        return rc
 
     def oct_optical_flow(self, geo1, geo2, nav: Nav, t1: float, t2: float, p: Optional[Params] = None,
                          cth=None, upix=None, vpix=None, nc: int = 1, out=None):
@@ -209,21 +237,26 @@ class Context:
 
     # ---- stage entry points (device pointers; parity tests)
     def stage_blur_decimate(self, d_img, nx, ny, nc, factor, d_out):
+        self._after_torch()
         self._check(self._L.octane_stage_blur_decimate(self._h, _ptr(d_img), nx, ny, nc, factor, _ptr(d_out)))
 
     def stage_gradient(self, d_f, xi, yi, nc, d_gx, d_gy):
+        self._after_torch()
         self._check(self._L.octane_stage_gradient(self._h, _ptr(d_f), xi, yi, nc, _ptr(d_gx), _ptr(d_gy)))
 
     def stage_zoom_in(self, d_flow, nx, ny, nxx, nyy, sf, d_out):
+        self._after_torch()
         self._check(self._L.octane_stage_zoom_in(self._h, _ptr(d_flow), nx, ny, nxx, nyy, sf, _ptr(d_out)))
 
     def stage_build(self, d_u, d_v, d_uh, d_vh, d_g1, d_g2, xi, yi, nc, p, lambdac, gnc, d_coef, d_bu, d_bv):
+        self._after_torch()
         self._check(self._L.octane_stage_build(self._h, _ptr(d_u), _ptr(d_v), _ptr(d_uh), _ptr(d_vh), _ptr(d_g1),
                                                _ptr(d_g2), xi, yi, nc, C.byref(p), lambdac, gnc, _ptr(d_coef),
                                                _ptr(d_bu), _ptr(d_bv)))
 
     def stage_pcg(self, d_coef, d_bu, d_bv, xi, yi, iters, tol, d_xu, d_xv) -> int:
         its = C.c_int()
+        self._after_torch()
         self._check(self._L.octane_stage_pcg(self._h, _ptr(d_coef), _ptr(d_bu), _ptr(d_bv), xi, yi, iters, tol,
                                              _ptr(d_xu), _ptr(d_xv), C.byref(its)))
         return its.value

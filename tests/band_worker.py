@@ -1,0 +1,77 @@
+"""Multi-GPU worker (launched by torch.distributed.run, one rank per GPU): solves one
+pair as row bands and compares with the single-GPU solve of the same pair on rank 0.
+Prints one line `BAND_RESULT {...json...}` on rank 0."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import octane_b200 as ob  # noqa: E402
+from octane_b200 import synthetic as S  # noqa: E402
+
+
+def main():
+    nx, ny = int(sys.argv[1]), int(sys.argv[2])
+    max_disp = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    p = ob.default_params(max_disp=max_disp)
+    ctx = ob.Context(local)
+    ids = [ob.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.comm_init(ids[0], rank, world)
+    own0, own1, in0, in1 = ob.band_plan(nx, ny, p, rank, world)
+    img1, img2 = S.make_pair_torch(nx, ny, 9, dev, rows=(in0, in1))
+    u = torch.zeros((own1 - own0, nx), device=dev); v = torch.zeros_like(u)
+    ctx.oct_variational_optical_flow_band(img1, img2, u, v, nx, ny, p)
+    ctx.synchronize()
+    st = ctx.stats()
+    # second run: bit-reproducible for a fixed world size
+    u2 = torch.zeros_like(u); v2 = torch.zeros_like(v)
+    ctx.oct_variational_optical_flow_band(img1, img2, u2, v2, nx, ny, p)
+    ctx.synchronize()
+    repro = bool(torch.equal(u, u2) and torch.equal(v, v2))
+    # navigation of the band
+    xs, ys, xo, yo, dt = S.SECTORS["conus_0.5km"]
+    nav = ob.goes_nav(xs, ys, xo, yo)
+    sh = [torch.zeros((own1 - own0, nx), dtype=torch.int16, device=dev) for _ in range(4)]
+    ctx.oct_pix2uv_band(nav, 0.0, dt, u, v, nx, own0, own1 - own0, *sh, p)
+    ctx.synchronize()
+    parts = [None] * world
+    dist.all_gather_object(parts, (own0, own1, u.cpu().numpy(), v.cpu().numpy(), sh[0].cpu().numpy(), repro,
+                                   list(st.cg_iterations[:st.n_solves])))
+    if rank == 0:
+        parts.sort(key=lambda t: t[0])
+        U = np.concatenate([t[2] for t in parts]); V = np.concatenate([t[3] for t in parts])
+        SU = np.concatenate([t[4] for t in parts])
+        # single-GPU reference on rank 0 with a fresh, un-banded context
+        c1 = ob.Context(local)
+        a, b = S.make_pair_torch(nx, ny, 9, dev)
+        u1 = torch.zeros((ny, nx), device=dev); v1 = torch.zeros_like(u1)
+        c1.oct_variational_optical_flow(a, b, u1, v1, ob.default_params(max_disp=max_disp))
+        s1 = [torch.zeros((ny, nx), dtype=torch.int16, device=dev) for _ in range(4)]
+        c1.oct_pix2uv_cuda(nav, 0.0, dt, u1, v1, *s1, p)
+        c1.synchronize()
+        st1 = c1.stats()
+        du = np.abs(U - u1.cpu().numpy()); dv = np.abs(V - v1.cpu().numpy())
+        res = dict(world=world, nx=nx, ny=ny, du_mean=float(du.mean()), du_max=float(du.max()), dv_mean=float(dv.mean()),
+                   dv_max=float(dv.max()), repro=all(t[5] for t in parts),
+                   its_equal=all(t[6] == list(st1.cg_iterations[:st1.n_solves]) for t in parts),
+                   nav_max=int(np.abs(SU.astype(int) - s1[0].cpu().numpy()).max()),
+                   bands=[(t[0], t[1]) for t in parts])
+        print("BAND_RESULT " + json.dumps(res), flush=True)
+        c1.close()
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
