@@ -1,0 +1,110 @@
+// oct_b200_shim.cc -- the reference-side binding of liboctane_b200.so.
+//
+// The reference has no FFI: its dispatcher (src/oct_optical_flow.cc:11-17)
+// declares the two hot-path functions by hand and links their objects.  This
+// file defines those two functions with the reference's EXACT C++ signatures
+//
+//   void oct_variational_optical_flow(Image, Image, float*, float*, float*, int, int, int, OFFlags)
+//        replaces src/oct_variational_optical_flow.cu:1213
+//   void oct_pix2uv_cuda(GOESVar&, double, float*, float*, short*, short*, short*, short*, OFFlags)
+//        replaces src/oct_pix2uv_cuda.cu:265
+//
+// on top of the C ABI in include/octane_b200.h, so that a maintainer drops the
+// two .cu objects from the reference's link line, adds this file and
+// -loctane_b200, and every caller above (oct_optical_flow.cc:67,91, main.cc:439)
+// stays unmodified.  It is compiled against the reference's own headers
+// (include/image.h, goesread.h, offlags.h) in the reference tree; nothing of
+// the reference is copied here.  INTEGRATION.md has the build line.
+//
+// Error behaviour mirrors the reference wrapper: no GPU -> message + exit(0)
+// (src/oct_variational_optical_flow.cu:1255-1259); any other failure, which the
+// reference ignores (:1421,1431), prints octane_last_error() and exit(1).
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+
+#include "image.h"      // before goesread.h, which uses Image without including it
+#include "goesread.h"
+#include "offlags.h"
+#include "octane_b200.h"
+
+namespace {
+
+octane_ctx* g_ctx[64] = { nullptr };
+
+octane_ctx* context_for(int device)
+{
+    const int n = octane_device_count();
+    if (n == 0) {
+        std::cout << "No gpus available for use, exiting\n";
+        exit(0);
+    }
+    if (device > n - 1 || device < 0) {
+        std::cout << "Warning: setdevice set to non-existent GPU, setting to default GPU 1\n";
+        device = 0;
+    }
+    if (device >= 64) device = 0;
+    if (!g_ctx[device]) {
+        int rc = octane_ctx_create(&g_ctx[device], device);
+        if (rc) {
+            fprintf(stderr, "octane_b200: %s\n", octane_last_error());
+            exit(rc == OCTANE_ENODEV ? 0 : 1);
+        }
+    }
+    return g_ctx[device];
+}
+
+void params_from(const OFFlags& a, octane_params* p)
+{
+    octane_params_default(p);
+    p->alpha = a.alpha; p->lambda = a.lambda; p->lambdac = a.lambdac;      // :1229-1241
+    p->scaleF = a.scaleF; p->scsig = a.scsig;
+    p->kiters = a.kiters; p->liters = a.liters; p->cgiters = a.cgiters;
+    p->dozim = a.dozim; p->setdevice = a.setdevice;
+    p->pixuv = a.pixuv; p->dopolar = a.dopolar; p->domerc = a.domerc;     // src/oct_pix2uv_cuda.cu:291-297
+    // The reference always reads uarr/varr as the first guess (:1330-1335); its only caller
+    // (src/oct_optical_flow.cc:38-53) passes zeros unless -firstguess was given, and a zero
+    // first guess is what first_guess = 0 means in the C ABI (no extra planes, same result).
+    p->first_guess = (a.dofirstguess != 0);
+    p->doCTH = a.doCTH; p->ir = a.ir;
+}
+
+void die(const char* what)
+{
+    fprintf(stderr, "octane_b200 %s: %s\n", what, octane_last_error());
+    exit(1);
+}
+
+}  // namespace
+
+void oct_variational_optical_flow(Image geo1i, Image geo2i, float* /*CTHarr: unused, dodiscrete=false :1302*/,
+                                  float* uarr, float* varr, int nx, int ny, int nc, OFFlags args)
+{
+    octane_params p;
+    params_from(args, &p);
+    octane_ctx* c = context_for(args.setdevice);
+    if (octane_variational_flow(c, geo1i.data, geo2i.data, nx, ny, nc, &p, uarr, varr) < 0)
+        die("oct_variational_optical_flow");
+}
+
+void oct_pix2uv_cuda(GOESVar& goesData, double t2, float* uarr, float* varr, short* ur, short* vr, short* ur2,
+                     short* vr2, OFFlags args)
+{
+    octane_params p;
+    params_from(args, &p);
+    octane_ctx* c = context_for(args.setdevice);
+    const GOESNAVVar& g = goesData.nav;
+    octane_nav nav;
+    nav.pph = g.pph; nav.req = g.req; nav.rpol = g.rpol; nav.lam0 = g.lam0;
+    nav.xScale = g.xScale; nav.xOffset = g.xOffset; nav.yScale = g.yScale; nav.yOffset = g.yOffset;
+    nav.g2xOffset = g.g2xOffset; nav.g2yOffset = g.g2yOffset;
+    nav.lat1 = g.lat1; nav.lon1 = g.lon1; nav.lon0 = g.lon0; nav.R = g.R;
+    nav.minX = g.minX; nav.minY = g.minY;
+    float dT = 0.f;
+    int rc = octane_pix2uv(c, &nav, goesData.t, t2, uarr, varr, (int)g.nx, (int)g.ny, &p, ur, vr, ur2, vr2, &dT);
+    if (rc < 0) die("oct_pix2uv_cuda");
+    if (rc == 1)
+        std::cout << "MOVE WARNING: Sector Moved, setting motions to 0 " << g.xOffset << " " << g.g2xOffset << " "
+                  << g.yOffset << " " << g.g2yOffset << std::endl;
+    goesData.dT = dT;          // src/oct_pix2uv_cuda.cu:347,357,369
+}

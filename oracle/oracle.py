@@ -172,6 +172,40 @@ def ref_cuda():
     return _ref_cuda
 
 
+_ref_shim = None
+
+
+def ref_shim():
+    """The reference's UNMODIFIED dispatcher object (oct_optical_flow.cc) linked against
+    octane_b200/shim/oct_b200_shim.cc + liboctane_b200.so: the drop-in proof."""
+    global _ref_shim
+    if _ref_shim is None:
+        L = C.CDLL(os.path.join(HERE, "_ref", "libref_shim.so"))
+        L.ref_optical_flow.argtypes = ref_cuda_argtypes()
+        _ref_shim = L
+    return _ref_shim
+
+
+def ref_cuda_argtypes():
+    return [_f32, _f32, C.c_void_p, C.c_int, C.c_int, C.POINTER(RefNav), C.c_double, C.c_double,
+            C.POINTER(RefParams), _f32, _f32, _i16, _i16, _i16, _i16, C.c_void_p, C.POINTER(C.c_float)]
+
+
+def ref_dispatch(L, img1, img2, nav, t1, t2, rp=None, cth=None):
+    """oct_optical_flow() of library L (ref_cuda() or ref_shim()) on host arrays."""
+    rp = rp or ref_params()
+    img1 = np.ascontiguousarray(img1, np.float32); img2 = np.ascontiguousarray(img2, np.float32)
+    ny, nx = img1.shape
+    up = np.zeros((ny, nx), np.float32); vp = np.zeros((ny, nx), np.float32)
+    o = [np.zeros((ny, nx), np.int16) for _ in range(4)]
+    ctp = np.zeros((ny, nx), np.int16)
+    dT = C.c_float()
+    cthp = None if cth is None else np.ascontiguousarray(cth, np.float32).ctypes.data
+    L.ref_optical_flow(img1, img2, cthp, nx, ny, C.byref(nav), t1, t2, C.byref(rp), up, vp, *o,
+                       ctp.ctypes.data, C.byref(dT))
+    return dict(uPix=up, vPix=vp, U=o[0], V=o[1], U_raw=o[2], V_raw=o[3], CTP=ctp, dT=dT.value)
+
+
 def ref_variational(img1, img2, rp=None, u0=None, v0=None, nc=1):
     rp = rp or ref_params()
     img1 = np.ascontiguousarray(img1, np.float32); img2 = np.ascontiguousarray(img2, np.float32)
