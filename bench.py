@@ -35,7 +35,16 @@ WORKLOADS = {
     "meso500": (500, 500, "meso_2km", False),
 }
 METRIC = "flow Mpix/s"
-B_PASS1, B_PASS2 = 60.0, 64.0      # algorithmic bytes per pixel per launch
+# algorithmic bytes per pixel per launch: pass 1 reads r, p, x, a1, a2, a4, W, N
+# and writes p, q, x (68 B; 44 B in iteration 0 and 60 B in iteration 1 of a solve, where p / x do not
+# exist yet); pass 2 reads q, r, a1, a4 and writes r (32 B)
+B_PASS1, B_PASS1_IT0, B_PASS1_IT1, B_PASS2 = 68.0, 44.0, 60.0, 32.0
+
+
+def pass1_bytes(its):
+    """average pass-1 bytes per pixel per working launch over solves with `its` iterations each"""
+    tot = sum((B_PASS1_IT0 if n >= 1 else 0) + (B_PASS1_IT1 if n >= 2 else 0) + B_PASS1 * max(n - 2, 0) for n in its)
+    return tot / max(sum(its), 1)
 
 
 def peaks():
@@ -200,7 +209,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fulldisk", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="fulldisk", choices=sorted(WORKLOADS) + ["custom"])
+    ap.add_argument("--size", default=None, help="developer: NXxNY scene instead of a named workload (conus sector)")
     ap.add_argument("--seed", type=int, default=4)
     ap.add_argument("--ref-size", type=int, default=1000, help="crop edge of the --impl reference sample")
     ap.add_argument("--ref-cuda", action="store_true", help="also time the reference CUDA build (sm_100 recompile)")
@@ -208,6 +218,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--max-disp", type=int, default=64)
     args = ap.parse_args()
+    if args.size:
+        sx, sy = (int(t) for t in args.size.split("x"))
+        WORKLOADS["custom"] = (sx, sy, "conus_0.5km", False)
+        args.workload = "custom"
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -349,7 +363,9 @@ def main():
 
     # ---- roofline of the dominant kernel (finest-level PCG passes, timed live above)
     peak, peak_src = peaks()
-    k1 = B_PASS1 * st.finest_pixels / (st.finest_pass1_ms * 1e-3) / 1e9 if st.finest_pass1_ms > 0 else 0.0
+    its = list(st.cg_iterations[:st.n_solves])
+    b1 = pass1_bytes(its[-3 * p.liters:])          # the finest level's solves
+    k1 = b1 * st.finest_pixels / (st.finest_pass1_ms * 1e-3) / 1e9 if st.finest_pass1_ms > 0 else 0.0
     k2 = B_PASS2 * st.finest_pixels / (st.finest_pass2_ms * 1e-3) / 1e9 if st.finest_pass2_ms > 0 else 0.0
     dom = "pcg_pass2" if st.ms_pcg_pass2 >= st.ms_pcg_pass1 else "pcg_pass1"
     ach = k2 if dom == "pcg_pass2" else k1
@@ -359,7 +375,6 @@ def main():
             traffic = json.load(f).get(args.workload, {}).get(dom)
     except Exception:
         pass
-    its = list(st.cg_iterations[:st.n_solves])
     line = {
         "metric": METRIC, "value": mpix / (ms_step / 1e3), "unit": "Mpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -372,7 +387,7 @@ def main():
         "clocks": clocks, "gpu_launches": launches * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                     "bytes_per_pixel_per_launch": B_PASS2 if dom == "pcg_pass2" else B_PASS1,
+                     "bytes_per_pixel_per_launch": B_PASS2 if dom == "pcg_pass2" else b1,
                      "pixels_per_launch": int(st.finest_pixels),
                      "pass1": {"GB/s": k1, "avg_ms": st.finest_pass1_ms}, "pass2": {"GB/s": k2, "avg_ms": st.finest_pass2_ms},
                      "whole_step": {"algorithmic_GB": st.algorithmic_bytes * world / 1e9,

@@ -89,7 +89,7 @@ typedef struct octane_stats {
     int level_nx[16], level_ny[16];
     int cg_iterations[OCTANE_MAX_SOLVES]; /* PCG iterations actually executed per solve */
     long long kernel_launches;            /* our kernels launched by the last call */
-    double algorithmic_bytes;             /* sum_k N_k(100+3*liters*80) + 124*sum n_it*N_k */
+    double algorithmic_bytes;             /* compulsory HBM bytes of the call on this rank */
     /* profile mode (octane_ctx_set_profile): CUDA-event timings on our stream */
     double ms_total;                      /* whole call, device side */
     double ms_pyramid, ms_build, ms_pcg_pass1, ms_pcg_pass2, ms_update, ms_nav;
@@ -157,7 +157,10 @@ int octane_stage_gradient(octane_ctx* ctx, const float* d_f, int xi, int yi, int
                           float* d_gx, float* d_gy);
 int octane_stage_zoom_in(octane_ctx* ctx, const float* d_flow, int nx, int ny, int nxx, int nyy,
                          float sf, float* d_out);
-/* coef: 7 dense planes [a1,a2,a4,a5,a6,a7,a8] with the boundary merging applied */
+/* coef: 7 dense planes [a1,a2,a4,a5,a6,a7,a8] = the distinct entries of the reference's CSR rows
+ * with its boundary merging applied (src/oct_variational_optical_flow.cu:929-1077).  The library
+ * stores 5 of them (a5, a6 are their neighbours' a7, a8); octane_stage_build expands, and
+ * octane_stage_pcg expects a system of that structure (symmetric couplings, mirror-merged edges). */
 int octane_stage_build(octane_ctx* ctx, const float* d_u, const float* d_v,
                        const float* d_uh, const float* d_vh,
                        const float* d_g1, const float* d_g2, int xi, int yi, int nc,

@@ -3,9 +3,10 @@
 // Replaces the body of the inner loop of octConjugateGradient,
 // src/oct_variational_optical_flow.cu:611-1097 (reference tree): same
 // neighbourhoods, same warp/clamp rules, same float/double promotion points.
-// Instead of CSR arrays (12 nnz x 12 B per pixel) it stores the 7 distinct
-// coefficients per pixel with the reference's boundary merging applied, the
-// right-hand side, and seeds the PCG scalars (r0 = b because x0 = 0).
+// Instead of CSR arrays (12 nnz x 12 B per pixel) it stores 5 coefficients per
+// pixel (the 2x2 diagonal block and the couplings to i+1 and j+1; the other two
+// couplings are their neighbours' by symmetry), the right-hand side, and seeds
+// the PCG scalars (r0 = b because x0 = 0).
 #include "kernels.cuh"
 
 namespace octane {
@@ -158,19 +159,18 @@ k_build(LevelFields f, PcgBuffers b, Geom g, int ja, int jb, int da, int db, Bui
         float a1 = (float)((al1) * ((vr1) / alpha + lambdadalpha * (vr12) + lambdac + psistotq) + (1 - al1) * (psid * (vr1) + psid2 * vr12 + lambdac + psistot));
         float a2 = (float)((al1) * ((vr2) / alpha + lambdadalpha * vr22) + (1 - al1) * (psid * (vr2) + psid2 * vr22));
         float a4 = (float)((al1) * ((vr4) / alpha + lambdadalpha * vr42 + lambdac + psistotq) + (1 - al1) * (psid * (vr4) + psid2 * vr42 + lambdac + psistot));
-        float a5 = (float)(-1 * (al1 + (1 - al1) * (psis1)));
-        float a6 = (float)(-1 * (al1 + (1 - al1) * (psis2)));
         float a7 = (float)(-1 * (al1 + (1 - al1) * (psis3)));
         float a8 = (float)(-1 * (al1 + (1 - al1) * (psis4)));
-        // boundary-merged entries (:929-1077): the weight of a neighbour that does not
-        // exist is added to the opposite neighbour; the absent entry is stored as 0.
-        b.coef[0][l] = a1;
-        b.coef[1][l] = a2;
-        b.coef[2][l] = a4;
-        b.coef[3][l] = (ii > 0) ? ((ii < xi - 1) ? a5 : a5 + a7) : 0.f;
-        b.coef[4][l] = (jj > 0) ? ((jj < yi - 1) ? a6 : a6 + a8) : 0.f;
-        b.coef[5][l] = (ii < xi - 1) ? ((ii > 0) ? a7 : a7 + a5) : 0.f;
-        b.coef[6][l] = (jj < yi - 1) ? ((jj > 0) ? a8 : a8 + a6) : 0.f;
+        // Only the couplings to i+1 and j+1 are stored: a5(i,j) == a7(i-1,j) and
+        // a6(i,j) == a8(i,j-1) bit for bit (same expression, two commuted additions), and at a
+        // mirrored edge a5 == a7 (a6 == a8), so the boundary merging of :929-1077 -- the weight
+        // of an absent neighbour is added to the opposite one -- is a doubling that the PCG
+        // kernels apply on the fly (kernels.cuh, PcgBuffers).
+        b.coef[C_A1][l] = a1;
+        b.coef[C_A2][l] = a2;
+        b.coef[C_A4][l] = a4;
+        b.coef[C_W][l] = a7;
+        b.coef[C_N][l] = a8;
         // right-hand side, :1087-1092
         float uvt = f.uh ? __ldg(f.uh + l) : 0.f;
         float vvt = f.vh ? __ldg(f.vh + l) : 0.f;
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(1024) k_build_finish(PcgBuffers b, unsigned nb
         s->rz = (float)acc[1];
         s->rz_old = 0.f;
         s->pAp = 0.f;
+        s->alpha = 0.f;
         s->tol = tol;
         s->its = 0;
         s->done = !((float)acc[0] > tol);

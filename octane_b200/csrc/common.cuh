@@ -28,6 +28,7 @@ struct PcgScalars {
     float rz;       // z_k.r_k          (rkTzk == zktrk)
     float pAp;      // p.Ap             (pkTApk)
     float rr;       // r.r              (residc)
+    float alpha;    // rz/pAp of the last executed iteration (x += alpha p is applied one pass later)
     float tol;
     int done;       // stop rule satisfied: !(rr > tol)
     int its;        // iterations executed in this solve

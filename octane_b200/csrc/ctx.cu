@@ -199,9 +199,11 @@ size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t arena_layout(const Plan& pl, Buffers* b, char* base)
 {
     size_t off = 0;
+    // developer switch for address-translation experiments: spread the planes over more memory
+    static const size_t pad = getenv("OCTANE_PLANE_PAD_MB") ? (size_t)atol(getenv("OCTANE_PLANE_PAD_MB")) << 20 : 0;
     auto take = [&](size_t nfloats) -> float* {
         float* p = base ? (float*)(base + off) : nullptr;
-        off += align_up(nfloats * sizeof(float));
+        off += align_up(nfloats * sizeof(float)) + pad;
         return p;
     };
     const size_t P = pl.P, Pc = pl.Pc, nc = pl.nc;
@@ -214,7 +216,7 @@ size_t arena_layout(const Plan& pl, Buffers* b, char* base)
     B.u = take(P); B.v = take(P); B.ut = take(Pc); B.vt = take(Pc);
     if (pl.p.first_guess) { B.uh = take(P); B.vh = take(P); B.hu = take(Pc); B.hv = take(Pc); }
     else { B.uh = B.vh = B.hu = B.hv = nullptr; }
-    for (int i = 0; i < 7; i++) B.pcg.coef[i] = take(P);
+    for (int i = 0; i < NCOEF; i++) B.pcg.coef[i] = take(P);
     B.pcg.ru = take(P); B.pcg.rv = take(P); B.pcg.xu = take(P); B.pcg.xv = take(P);
     B.pcg.pu[0] = take(P); B.pcg.pu[1] = take(P); B.pcg.pv[0] = take(P); B.pcg.pv[1] = take(P);
     B.pcg.qu = take(P); B.pcg.qv = take(P);
@@ -349,14 +351,13 @@ int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve)
     const PcgBuffers& b = c->buf.pcg;
     const int iters = c->plan.p.cgiters;
     const bool multi = c->comm.world > 1;
-    int cur = 0;
     for (int ki = 0; ki < iters; ki++) {
         {
             Scope s(c, CAT_P1, level, solve, ki);
             if (c->use_tma && pcg_pass1_tma_usable(L.g, L.own1 - L.own0))
-                launch_pcg_pass1_tma(b, L.g, L.own0, L.own1, ki == 0, cur, multi, c->sm_count, c->stream);
+                launch_pcg_pass1_tma(b, L.g, L.own0, L.own1, ki, multi, c->sm_count, c->stream);
             else
-                launch_pcg_pass1(b, L.g, L.own0, L.own1, ki == 0, cur, multi, c->sm_count, c->stream);
+                launch_pcg_pass1(b, L.g, L.own0, L.own1, ki, multi, c->sm_count, c->stream);
             c->launches++;
         }
         if (multi) {
@@ -365,7 +366,7 @@ int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve)
         }
         {
             Scope s(c, CAT_P2, level, solve, ki);
-            launch_pcg_pass2(b, L.g, L.own0, L.own1, ki == 0, cur, c->sm_count, c->stream);
+            launch_pcg_pass2(b, L.g, L.own0, L.own1, c->sm_count, c->stream);
             c->launches++;
         }
         if (multi) {
@@ -374,7 +375,6 @@ int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve)
             float* planes[2] = { b.ru, b.rv };            // next pass 1 rebuilds p on the halo rows from r
             rc = exchange_rows(c, L, 2, planes, 1); if (rc) return rc;
         }
-        cur ^= 1;
     }
     return OCTANE_OK;
 }
@@ -491,8 +491,7 @@ int run_levels(octane_ctx* c)
                 if (rc) return rc;
                 {
                     Scope s(c, CAT_UPDATE, k, solve);             // :1185-1195
-                    launch_update_uv(B.u, B.v, B.pcg.xu, B.pcg.xv, g, L.own0, L.own1, c->d_scal,
-                                     c->d_its + solve, c->sm_count, st);
+                    launch_update_uv(B.u, B.v, B.pcg, g, L.own0, L.own1, c->d_its + solve, c->sm_count, st);
                     c->launches++;
                     float* planes[2] = { B.u, B.v };
                     rc = exchange_rows(c, L, 2, planes, HALO_UV); if (rc) return rc;
@@ -629,10 +628,16 @@ void collect_stats(octane_ctx* c)
         const Level& L = pl.lv[k];
         s.level_nx[k] = L.g.nx; s.level_ny[k] = L.g.ny;
         const double Nk = (double)L.g.nx * (L.own1 - L.own0);
-        bytes += Nk * (100.0 + 3.0 * pl.p.liters * 80.0);
+        // DESIGN.md "algorithmic bytes": pyramid 100 B/px per level; per solve the build
+        // (72 B/px), pass 1 (44 / 60 / 68 B/px for iteration 0 / 1 / later), pass 2 (32 B/px)
+        // for the iterations actually executed, and the u,v update (32 B/px)
+        bytes += Nk * 100.0;
         for (int q = 0; q < 3 * pl.p.liters; q++, solve++) {
-            s.cg_iterations[solve] = c->h_its[solve];
-            bytes += 124.0 * Nk * c->h_its[solve];
+            const int n = c->h_its[solve];
+            s.cg_iterations[solve] = n;
+            double per = 72.0 + 32.0 * n + (n >= 1 ? 44.0 : 0.0) + (n >= 2 ? 60.0 : 0.0) + (n > 2 ? 68.0 * (n - 2) : 0.0);
+            if (n >= 1) per += 32.0;
+            bytes += Nk * per;
         }
     }
     s.algorithmic_bytes = bytes;
@@ -1041,7 +1046,12 @@ int octane_stage_build(octane_ctx* c, const float* d_u, const float* d_v, const 
     bp.alpha = p->alpha; bp.lambdadalpha = p->lambda / p->alpha; bp.lambdac = lambdac_level;
     bp.dozim = p->dozim != 0; bp.nchan = nc; bp.tol = 0.0001 * 0.0001; bp.al1 = 1. - 0.5 * gnc;
     launch_build(f, B.pcg, g, 0, yi, 0, yi, bp, 0, st);
-    for (int k = 0; k < 7; k++) if ((rc = copy_out(c, d_coef + (size_t)k * xi * yi, B.pcg.coef[k], g))) return rc;
+    // the 7 boundary-merged entries of the reference, expanded from the 5 stored planes
+    // (scratch: the PCG vectors, which the build does not touch)
+    float* e[4] = { B.pcg.pu[0], B.pcg.pv[0], B.pcg.pu[1], B.pcg.pv[1] };
+    launch_expand_coef(B.pcg, g, e[0], e[1], e[2], e[3], st);
+    const float* src7[7] = { B.pcg.coef[C_A1], B.pcg.coef[C_A2], B.pcg.coef[C_A4], e[0], e[1], e[2], e[3] };
+    for (int k = 0; k < 7; k++) if ((rc = copy_out(c, d_coef + (size_t)k * xi * yi, src7[k], g))) return rc;
     if ((rc = copy_out(c, d_bu, B.pcg.ru, g))) return rc;
     if ((rc = copy_out(c, d_bv, B.pcg.rv, g))) return rc;
     CUDA_OK(cudaGetLastError());
@@ -1058,16 +1068,23 @@ __global__ void k_seed_scalars(PcgBuffers b, Geom g, float tol)
         for (int i = threadIdx.x; i < g.nx; i += blockDim.x) {
             const size_t l = g.at(i, j);
             const float bu = b.ru[l], bv = b.rv[l];
-            const float mu = 1. / b.coef[0][l], mv = 1. / b.coef[2][l];
+            const float mu = 1. / b.coef[C_A1][l], mv = 1. / b.coef[C_A4][l];
             acc[0] += (double)(bu * bu) + (double)(bv * bv);
             acc[1] += (double)(bu * (mu * bu)) + (double)(bv * (mv * bv));
         }
     block_sum<2>(acc, red);
     if (threadIdx.x == 0) {
         PcgScalars* s = b.scal;
-        s->rr = (float)acc[0]; s->rz = (float)acc[1]; s->rz_old = 0.f; s->pAp = 0.f;
+        s->rr = (float)acc[0]; s->rz = (float)acc[1]; s->rz_old = 0.f; s->pAp = 0.f; s->alpha = 0.f;
         s->tol = tol; s->its = 0; s->done = !((float)acc[0] > tol);
     }
+}
+
+__global__ void k_unmerge_edges(PcgBuffers b, Geom g)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < g.ny) b.coef[C_W][g.at(0, t)] *= 0.5f;                       // a7(0,j) = 2 W(0,j)
+    else if (t - g.ny < g.nx) b.coef[C_N][g.at(t - g.ny, 0)] *= 0.5f;    // a8(i,0) = 2 N(i,0)
 }
 
 int octane_stage_pcg(octane_ctx* c, const float* d_coef, const float* d_bu, const float* d_bv, int xi, int yi,
@@ -1082,7 +1099,12 @@ int octane_stage_pcg(octane_ctx* c, const float* d_coef, const float* d_bu, cons
     const Level& L = c->plan.lv[0];
     const Geom& g = L.g;
     cudaStream_t st = c->stream;
-    for (int k = 0; k < 7; k++) if ((rc = copy_in(c, B.pcg.coef[k], d_coef + (size_t)k * xi * yi, g, 1))) return rc;
+    // d_coef must be a system as the build produces it: symmetric couplings, mirror-merged
+    // edges.  W = a7 and N = a8 with the edge doubling undone (first column / first row).
+    const int src5[NCOEF] = { 0, 1, 2, 5, 6 };
+    for (int k = 0; k < NCOEF; k++)
+        if ((rc = copy_in(c, B.pcg.coef[k], d_coef + (size_t)src5[k] * xi * yi, g, 1))) return rc;
+    k_unmerge_edges<<<(xi + yi + 255) / 256, 256, 0, st>>>(B.pcg, g);
     if ((rc = copy_in(c, B.pcg.ru, d_bu, g, 1))) return rc;
     if ((rc = copy_in(c, B.pcg.rv, d_bv, g, 1))) return rc;
     k_seed_scalars<<<1, 1024, 0, st>>>(B.pcg, g, tol);
@@ -1090,7 +1112,7 @@ int octane_stage_pcg(octane_ctx* c, const float* d_coef, const float* d_bu, cons
     CUDA_OK(cudaMemsetAsync(B.v, 0, (size_t)g.plane * sizeof(float), st));
     begin_call(c);
     rc = run_pcg(c, L, 0, 0); if (rc) return rc;
-    launch_update_uv(B.u, B.v, B.pcg.xu, B.pcg.xv, g, 0, yi, c->d_scal, c->d_its, c->sm_count, st);   // u = 0 + x
+    launch_update_uv(B.u, B.v, B.pcg, g, 0, yi, c->d_its, c->sm_count, st);   // u = 0 + x
     if ((rc = copy_out(c, d_xu, B.u, g))) return rc;
     if ((rc = copy_out(c, d_xv, B.v, g))) return rc;
     CUDA_OK(cudaMemcpyAsync(c->h_its, c->d_its, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -19,8 +19,16 @@ struct LevelFields {           // device planes of one level, all sharing Geom g
     float *u, *v;                                    // current flow
     const float *uh, *vh;                            // hint (first guess at this level) or nullptr
 };
+// Coefficient storage.  The reference's 12 CSR entries per pixel (:868-1077) hold 7 distinct
+// values a1,a2,a4 (2x2 diagonal block) and a5..a8 (couplings to i-1, j-1, i+1, j+1).  The
+// couplings are symmetric bit for bit -- a5(i,j) == a7(i-1,j) and a6(i,j) == a8(i,j-1), the
+// half-point weights of :680-683 being the same expression with two commuted additions -- so
+// only W = a7 (to i+1) and N = a8 (to j+1) are stored, unmerged; the boundary merging of
+// :929-1077 (an absent neighbour's weight is added to the opposite one, which there equals
+// doubling it) is applied when the stencil is evaluated.
+enum { C_A1 = 0, C_A2 = 1, C_A4 = 2, C_W = 3, C_N = 4, NCOEF = 5 };
 struct PcgBuffers {
-    float* coef[7];            // a1,a2,a4,a5,a6,a7,a8 (boundary-merged)
+    float* coef[NCOEF];        // a1, a2, a4, W, N
     float *ru, *rv;            // rhs, then residual
     float *xu, *xv;            // solution increment
     float *pu[2], *pv[2];      // search direction, ping-pong
@@ -47,19 +55,23 @@ void launch_build(const LevelFields& f, const PcgBuffers& b, const Geom& g, int 
 int build_partial_blocks(const Geom& g, int nrows);
 
 // ---- pcg.cu
-// One PCG iteration = pass1 (p update fused with the stencil product, dot p.Ap)
-// + pass2 (x, r update, dots r.r and z.r, stop rule).  `cur` selects which of
-// the ping-pong p buffers holds p_old.
-void launch_pcg_pass1(const PcgBuffers& b, const Geom& g, int ja, int jb, int first, int cur, int store_halo,
+// One PCG iteration ki = pass1 (x += alpha_{ki-1} p_{ki-1}; p = z + beta p; q = A p; dot p.q)
+// + pass2 (r -= alpha q, dots r.r and z.r, stop rule).  The x update of an iteration rides
+// on the NEXT iteration's pass 1, which reads p_old anyway (saves one read of p per
+// iteration); launch_update_uv applies the last pending term.  Iteration ki reads
+// p[ki & 1] and writes p[(ki & 1) ^ 1].
+void launch_pcg_pass1(const PcgBuffers& b, const Geom& g, int ja, int jb, int ki, int store_halo,
                       int sm_count, cudaStream_t st);
 // large levels: persistent TMA-fed variant of pass 1 (pcg_tma.cu)
 bool pcg_pass1_tma_usable(const Geom& g, int nrows);
-void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, int first, int cur, int store_halo,
+void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, int ki, int store_halo,
                           int sm_count, cudaStream_t st);
-void launch_pcg_pass2(const PcgBuffers& b, const Geom& g, int ja, int jb, int first, int cur, int sm_count,
-                      cudaStream_t st);
-void launch_update_uv(float* u, float* v, const float* xu, const float* xv, const Geom& g, int ja, int jb,
-                      const PcgScalars* s, int* its_out, int sm_count, cudaStream_t st);
+void launch_pcg_pass2(const PcgBuffers& b, const Geom& g, int ja, int jb, int sm_count, cudaStream_t st);
+// u += x + alpha_last p_last, v likewise (:1185-1195 with the pending x term folded in)
+void launch_update_uv(float* u, float* v, const PcgBuffers& b, const Geom& g, int ja, int jb,
+                      int* its_out, int sm_count, cudaStream_t st);
+// test hooks: 5-plane storage <-> the reference's 7 boundary-merged entries
+void launch_expand_coef(const PcgBuffers& b, const Geom& g, float* a5, float* a6, float* a7, float* a8, cudaStream_t st);
 // dense (stride nx, rows [ja,jb) starting at src row 0) <-> pitched
 void launch_scale_copy(const float* src, float* dst, const Geom& g, int ja, int jb, float scale, cudaStream_t st);
 

@@ -4,11 +4,12 @@
 // (reference tree).  The reference spends ~12 grid-wide barriers and ~520 B/px
 // per iteration on explicit CSR; here one iteration is two streaming kernels:
 //
-//   pass 1  p = z + beta p   (z = M^-1 r, recomputed, never stored)
+//   pass 1  x += alpha' p   (the PREVIOUS iteration's update: p is being read anyway)
+//           p = z + beta p   (z = M^-1 r, recomputed, never stored)
 //           q = A p          (stencil, rolling three rows of p in registers)
-//           partial p.q                                   60 B/px
-//   pass 2  x += alpha p ; r -= alpha q ; partial r.r and z.r
-//           stop rule + scalar roll in the last block      64 B/px
+//           partial p.q                                   68 B/px
+//   pass 2  r -= alpha q ; partial r.r and z.r
+//           stop rule + scalar roll in the last block      32 B/px
 //
 // Same recurrence, same fp32 scalar arithmetic (alpha = rz/pAp, beta =
 // rz_new/rz_old, stop on !(r.r > tol) or the launch cap), same FMA order inside
@@ -31,6 +32,10 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 __device__ __forceinline__ float& el(float4& v, int k) { return reinterpret_cast<float*>(&v)[k]; }
 __device__ __forceinline__ const float& el(const float4& v, int k) { return reinterpret_cast<const float*>(&v)[k]; }
 
+// x-update mode of a pass-1 launch: iteration 0 has no previous term; iteration 1 starts x
+// (x = alpha_0 p_0, no read of x); later iterations accumulate.
+enum { XM_NONE = 0, XM_INIT = 1, XM_ACC = 2 };
+
 struct P1Args {
     PcgBuffers b;
     Geom g;
@@ -47,12 +52,15 @@ struct PRow {
     float eu, ev;      // p_new of the pixel just outside the warp's strip (lanes 0 and 31)
 };
 
-// p_new = (1/M) r + beta p_old for one row segment of the warp's strip.
+// p_new = (1/M) r + beta p_old for one row segment of the warp's strip; when `own`, also the
+// pending x += alpha_prev p_old of the previous iteration (:1172) for the same pixels.
 // (1/M) as jDiagInv (:142-149): 1./M rounded to float; z = Minv*r (:1117,1138);
 // p = Bk*p + z (:1146, one FMA).
-template <bool FIRST>
-__device__ __forceinline__ PRow compute_p(const P1Args& a, int j, int i0, int lane, float beta)
+template <int XM>
+__device__ __forceinline__ PRow compute_p(const P1Args& a, int j, int i0, int lane, float beta, float alpha_prev,
+                                          bool own)
 {
+    constexpr bool FIRST = (XM == XM_NONE);
     PRow o;
     o.pu = o.pv = o.a1 = o.a4 = make_float4(0.f, 0.f, 0.f, 0.f);
     o.eu = o.ev = 0.f;
@@ -63,10 +71,25 @@ __device__ __forceinline__ PRow compute_p(const P1Args& a, int j, int i0, int la
     if (i0 < g.nx) {
         const size_t off = g.at(i0, j);
         const float4 ru = ld4(a.b.ru + off), rv = ld4(a.b.rv + off);
-        o.a1 = ld4(a.b.coef[0] + off);
-        o.a4 = ld4(a.b.coef[2] + off);
+        o.a1 = ld4(a.b.coef[C_A1] + off);
+        o.a4 = ld4(a.b.coef[C_A4] + off);
         float4 po_u = make_float4(0.f, 0.f, 0.f, 0.f), po_v = po_u;
         if (!FIRST) { po_u = ld4(pu_old + off); po_v = ld4(pv_old + off); }
+        if (!FIRST && own) {
+            float4 x_u = make_float4(0.f, 0.f, 0.f, 0.f), x_v = x_u;
+            if (XM == XM_ACC) { x_u = ld4(a.b.xu + off); x_v = ld4(a.b.xv + off); }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (i0 + k < g.nx) {
+                    el(x_u, k) = fmaf(alpha_prev, el(po_u, k), el(x_u, k));      // :1172
+                    el(x_v, k) = fmaf(alpha_prev, el(po_v, k), el(x_v, k));
+                } else {
+                    el(x_u, k) = 0.f; el(x_v, k) = 0.f;
+                }
+            }
+            st4(a.b.xu + off, x_u);
+            st4(a.b.xv + off, x_v);
+        }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (i0 + k < g.nx) {
@@ -81,7 +104,7 @@ __device__ __forceinline__ PRow compute_p(const P1Args& a, int j, int i0, int la
         const int ie = (lane == 0) ? i0 - 1 : i0 + 4;
         if (ie >= 0 && ie < g.nx) {
             const size_t off = g.at(ie, j);
-            const float mu = 1.0f / a.b.coef[0][off], mv = 1.0f / a.b.coef[2][off];
+            const float mu = 1.0f / a.b.coef[C_A1][off], mv = 1.0f / a.b.coef[C_A4][off];
             const float zu = mu * a.b.ru[off], zv = mv * a.b.rv[off];
             o.eu = FIRST ? zu : fmaf(beta, pu_old[off], zu);
             o.ev = FIRST ? zv : fmaf(beta, pv_old[off], zv);
@@ -90,18 +113,27 @@ __device__ __forceinline__ PRow compute_p(const P1Args& a, int j, int i0, int la
     return o;
 }
 
-template <bool FIRST>
+// boundary merging of the stored couplings (:929-1077): multiplier of W(i-1) / W(i) as the
+// entry towards i-1 / i+1 of pixel i (and the same in j for N)
+__device__ __forceinline__ float mul_lo(int i, int n) { return i == 0 ? 0.f : (i == n - 1 ? 2.f : 1.f); }
+__device__ __forceinline__ float mul_hi(int i, int n) { return i == n - 1 ? 0.f : (i == 0 ? 2.f : 1.f); }
+
+template <int XM>
 __global__ void __launch_bounds__(256, 2) k_pcg_pass1(P1Args a)
 {
+    constexpr bool FIRST = (XM == XM_NONE);
     __shared__ double red[32];
     const PcgScalars* s = a.b.scal;
     if (s->done) return;
     const float beta = FIRST ? 0.f : s->rz / s->rz_old;      // Bk, :1144
+    const float alpha_prev = FIRST ? 0.f : s->alpha;
     const Geom& g = a.g;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int ntasks = a.nstrips * a.nsegs;
     float* pu_new = a.b.pu[a.cur ^ 1];
     float* pv_new = a.b.pv[a.cur ^ 1];
+    const float* W = a.b.coef[C_W];
+    const float* N = a.b.coef[C_N];
     double dot[1] = { 0.0 };
 
     for (int t = blockIdx.x * 8 + wib; t < ntasks; t += gridDim.x * 8) {
@@ -109,46 +141,58 @@ __global__ void __launch_bounds__(256, 2) k_pcg_pass1(P1Args a)
         const int i0 = strip * 128 + lane * 4;
         const int j_a = a.ja + seg * a.rs, j_b = min(a.jb, j_a + a.rs);
         const bool active = i0 < g.nx;
-        PRow up = compute_p<FIRST>(a, j_a - 1, i0, lane, beta);
-        PRow ce = compute_p<FIRST>(a, j_a, i0, lane, beta);
+        PRow up = compute_p<XM>(a, j_a - 1, i0, lane, beta, alpha_prev, false);
+        PRow ce = compute_p<XM>(a, j_a, i0, lane, beta, alpha_prev, true);
+        float4 n_up = make_float4(0.f, 0.f, 0.f, 0.f);                 // N of the row above the centre
+        if (active && j_a > 0) n_up = ld4(N + g.at(i0, j_a - 1));
         if (a.store_halo && j_a == a.ja && j_a - 1 >= 0 && active) {
             st4(pu_new + g.at(i0, j_a - 1), up.pu);
             st4(pv_new + g.at(i0, j_a - 1), up.pv);
         }
         for (int j = j_a; j < j_b; j++) {
-            PRow dn = compute_p<FIRST>(a, j + 1, i0, lane, beta);
+            PRow dn = compute_p<XM>(a, j + 1, i0, lane, beta, alpha_prev, j + 1 < j_b);
             // horizontal neighbours of the centre row: lanes exchange their edge pixels
             float lu = __shfl_up_sync(0xffffffffu, ce.pu.w, 1), lv = __shfl_up_sync(0xffffffffu, ce.pv.w, 1);
             float ru_ = __shfl_down_sync(0xffffffffu, ce.pu.x, 1), rv_ = __shfl_down_sync(0xffffffffu, ce.pv.x, 1);
             if (lane == 0) { lu = ce.eu; lv = ce.ev; }
             if (lane == 31) { ru_ = ce.eu; rv_ = ce.ev; }
+            float4 a2 = make_float4(0.f, 0.f, 0.f, 0.f), w = a2, nn = a2;
+            size_t off = 0;
             if (active) {
-                const size_t off = g.at(i0, j);
-                const float4 a2 = ld4_stream(a.b.coef[1] + off), a5 = ld4_stream(a.b.coef[3] + off),
-                             a6 = ld4_stream(a.b.coef[4] + off), a7 = ld4_stream(a.b.coef[5] + off),
-                             a8 = ld4_stream(a.b.coef[6] + off);
+                off = g.at(i0, j);
+                a2 = ld4_stream(a.b.coef[C_A2] + off);
+                w = ld4_stream(W + off);
+                nn = ld4_stream(N + off);
+            }
+            float wl = __shfl_up_sync(0xffffffffu, w.w, 1);            // W of the pixel left of the lane's first
+            if (lane == 0) wl = (active && i0 > 0) ? W[off - 1] : 0.f;
+            if (active) {
+                const float m6 = mul_lo(j, g.ny), m8 = mul_hi(j, g.ny);
                 float4 qu, qv;
                 float part = 0.f;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const float pl_u = (k == 0) ? lu : el(ce.pu, k - 1), pl_v = (k == 0) ? lv : el(ce.pv, k - 1);
                     const float pr_u = (k == 3) ? ru_ : el(ce.pu, k + 1), pr_v = (k == 3) ? rv_ : el(ce.pv, k + 1);
+                    const float a5 = mul_lo(i0 + k, g.nx) * ((k == 0) ? wl : el(w, k - 1));
+                    const float a7 = mul_hi(i0 + k, g.nx) * el(w, k);
+                    const float a6 = m6 * el(n_up, k), a8 = m8 * el(nn, k);
                     // row of u: [j-1] [i-1] a1 a2 [i+1] [j+1]   (multiply_row order)
                     float su = 0.f;
-                    su = fmaf(el(a6, k), el(up.pu, k), su);
-                    su = fmaf(el(a5, k), pl_u, su);
+                    su = fmaf(a6, el(up.pu, k), su);
+                    su = fmaf(a5, pl_u, su);
                     su = fmaf(el(ce.a1, k), el(ce.pu, k), su);
                     su = fmaf(el(a2, k), el(ce.pv, k), su);
-                    su = fmaf(el(a7, k), pr_u, su);
-                    su = fmaf(el(a8, k), el(dn.pu, k), su);
+                    su = fmaf(a7, pr_u, su);
+                    su = fmaf(a8, el(dn.pu, k), su);
                     // row of v: [j-1] [i-1] a2 a4 [i+1] [j+1]
                     float sv = 0.f;
-                    sv = fmaf(el(a6, k), el(up.pv, k), sv);
-                    sv = fmaf(el(a5, k), pl_v, sv);
+                    sv = fmaf(a6, el(up.pv, k), sv);
+                    sv = fmaf(a5, pl_v, sv);
                     sv = fmaf(el(a2, k), el(ce.pu, k), sv);
                     sv = fmaf(el(ce.a4, k), el(ce.pv, k), sv);
-                    sv = fmaf(el(a7, k), pr_v, sv);
-                    sv = fmaf(el(a8, k), el(dn.pv, k), sv);
+                    sv = fmaf(a7, pr_v, sv);
+                    sv = fmaf(a8, el(dn.pv, k), sv);
                     const bool in = i0 + k < g.nx;
                     el(qu, k) = in ? su : 0.f;
                     el(qv, k) = in ? sv : 0.f;
@@ -160,6 +204,7 @@ __global__ void __launch_bounds__(256, 2) k_pcg_pass1(P1Args a)
                 st4(a.b.qv + off, qv);
                 dot[0] += (double)part;
             }
+            n_up = nn;
             up = ce;
             ce = dn;
         }
@@ -182,10 +227,9 @@ struct P2Args {
     PcgBuffers b;
     Geom g;
     int ja, jb;
-    int cur;           // pass 1 of this iteration wrote p[cur^1]
 };
 
-template <bool FIRST>
+// r -= alpha q; partial r.r and z.r; the last block rolls the scalars and applies the stop rule.
 __global__ void __launch_bounds__(256) k_pcg_pass2(P2Args a)
 {
     __shared__ double red[2 * 32];
@@ -194,8 +238,6 @@ __global__ void __launch_bounds__(256) k_pcg_pass2(P2Args a)
     const float alphak = s->rz / s->pAp;                      // :1169
     const float nalpha = -1. * alphak;                        // :1174
     const Geom& g = a.g;
-    const float* pu = a.b.pu[a.cur ^ 1];
-    const float* pv = a.b.pv[a.cur ^ 1];
     const int upr = g.pitch >> 2;                             // float4 units per row
     const long long nunits = (long long)(a.jb - a.ja) * upr;
     double acc[2] = { 0.0, 0.0 };
@@ -203,18 +245,13 @@ __global__ void __launch_bounds__(256) k_pcg_pass2(P2Args a)
         const int jr = (int)(t / upr), i0 = (int)(t - (long long)jr * upr) * 4;
         if (i0 >= g.nx) continue;
         const size_t off = g.at(i0, a.ja + jr);
-        const float4 p_u = ld4(pu + off), p_v = ld4(pv + off);
         const float4 q_u = ld4_stream(a.b.qu + off), q_v = ld4_stream(a.b.qv + off);
         float4 r_u = ld4(a.b.ru + off), r_v = ld4(a.b.rv + off);
-        const float4 a1 = ld4(a.b.coef[0] + off), a4 = ld4(a.b.coef[2] + off);
-        float4 x_u = make_float4(0.f, 0.f, 0.f, 0.f), x_v = x_u;
-        if (!FIRST) { x_u = ld4(a.b.xu + off); x_v = ld4(a.b.xv + off); }
+        const float4 a1 = ld4(a.b.coef[C_A1] + off), a4 = ld4(a.b.coef[C_A4] + off);
         float prr = 0.f, prz = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (i0 + k < g.nx) {
-                el(x_u, k) = fmaf(alphak, el(p_u, k), el(x_u, k));       // :1172
-                el(x_v, k) = fmaf(alphak, el(p_v, k), el(x_v, k));
                 const float ru = fmaf(nalpha, el(q_u, k), el(r_u, k));   // :1174
                 const float rv = fmaf(nalpha, el(q_v, k), el(r_v, k));
                 el(r_u, k) = ru;
@@ -223,11 +260,9 @@ __global__ void __launch_bounds__(256) k_pcg_pass2(P2Args a)
                 prr += ru * ru + rv * rv;                                // residc, :1178
                 prz += zu * ru + zv * rv;                                // zktrk of the next iteration, :1142
             } else {
-                el(x_u, k) = 0.f; el(x_v, k) = 0.f; el(r_u, k) = 0.f; el(r_v, k) = 0.f;
+                el(r_u, k) = 0.f; el(r_v, k) = 0.f;
             }
         }
-        st4(a.b.xu + off, x_u);
-        st4(a.b.xv + off, x_v);
         st4(a.b.ru + off, r_u);
         st4(a.b.rv + off, r_v);
         acc[0] += (double)prr;
@@ -241,6 +276,7 @@ __global__ void __launch_bounds__(256) k_pcg_pass2(P2Args a)
             a.b.pending[1] = tot[1];
         } else if (threadIdx.x == 0) {
             const float rr = (float)tot[0];
+            s->alpha = alphak;                 // x += alpha p rides on the next pass 1 / the final update
             s->rz_old = s->rz;                 // z0tr0 of the next iteration, :1135
             s->rz = (float)tot[1];
             s->rr = rr;
@@ -260,6 +296,7 @@ __global__ void k_finalize(PcgBuffers b, int kind, float tol)
         s->rz = (float)b.pending[1];
         s->rz_old = 0.f;
         s->pAp = 0.f;
+        s->alpha = 0.f;
         s->tol = tol;
         s->its = 0;
         s->done = !((float)b.pending[0] > tol);
@@ -270,6 +307,7 @@ __global__ void k_finalize(PcgBuffers b, int kind, float tol)
         s->pAp = (float)b.pending[0];
     } else {
         const float rr = (float)b.pending[0];
+        s->alpha = s->rz / s->pAp;             // what every block of pass 2 just used
         s->rz_old = s->rz;
         s->rz = (float)b.pending[1];
         s->rr = rr;
@@ -283,27 +321,55 @@ void launch_finalize(const PcgBuffers& b, int kind, float tol, cudaStream_t st)
     k_finalize<<<1, 1, 0, st>>>(b, kind, tol);
 }
 
-// u += x, v += x after a solve (:1185-1195); x is undefined when no iteration ran.
+// u += x, v += x after a solve (:1185-1195), with the last pending x += alpha p folded in.
+// After `its` iterations x holds the terms of iterations 0 .. its-2 (none when its == 1) and
+// p[its & 1] is the search direction of iteration its-1.  Nothing happens when no iteration ran.
 __global__ void __launch_bounds__(256)
-k_update_uv(float* __restrict__ u, float* __restrict__ v, const float* __restrict__ xu,
-            const float* __restrict__ xv, Geom g, int ja, int jb, const PcgScalars* s, int* its_out)
+k_update_uv(float* __restrict__ u, float* __restrict__ v, PcgBuffers b, Geom g, int ja, int jb, int* its_out)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && its_out) *its_out = s->its;
-    if (s->its == 0) return;
+    const PcgScalars* s = b.scal;
+    const int its = s->its;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && its_out) *its_out = its;
+    if (its == 0) return;
+    const float alpha = s->alpha;
+    const float* pu = b.pu[its & 1];
+    const float* pv = b.pv[its & 1];
     const int upr = g.pitch >> 2;
     const long long nunits = (long long)(jb - ja) * upr;
     for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < nunits; t += (long long)gridDim.x * 256) {
         const int jr = (int)(t / upr), i0 = (int)(t - (long long)jr * upr) * 4;
         if (i0 >= g.nx) continue;
         const size_t off = g.at(i0, ja + jr);
-        float4 a = ld4(u + off), b = ld4(v + off);
-        const float4 c = ld4(xu + off), d = ld4(xv + off);
+        float4 a = ld4(u + off), c = ld4(v + off);
+        float4 xu = make_float4(0.f, 0.f, 0.f, 0.f), xv = xu;
+        if (its > 1) { xu = ld4(b.xu + off); xv = ld4(b.xv + off); }
+        const float4 p_u = ld4(pu + off), p_v = ld4(pv + off);
 #pragma unroll
         for (int k = 0; k < 4; k++)
-            if (i0 + k < g.nx) { el(a, k) = el(a, k) + el(c, k); el(b, k) = el(b, k) + el(d, k); }
+            if (i0 + k < g.nx) {
+                const float x1 = fmaf(alpha, el(p_u, k), el(xu, k));     // :1172 of the last iteration
+                const float x2 = fmaf(alpha, el(p_v, k), el(xv, k));
+                el(a, k) = el(a, k) + x1;                                // :1187-1188
+                el(c, k) = el(c, k) + x2;
+            }
         st4(u + off, a);
-        st4(v + off, b);
+        st4(v + off, c);
     }
+}
+
+// test hook: the reference's boundary-merged a5..a8 from the stored W, N
+__global__ void __launch_bounds__(256)
+k_expand_coef(PcgBuffers b, Geom g, float* a5, float* a6, float* a7, float* a8)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x, j = blockIdx.y;
+    if (i >= g.nx || j >= g.ny) return;
+    const size_t l = g.at(i, j);
+    const float* W = b.coef[C_W];
+    const float* N = b.coef[C_N];
+    a5[l] = mul_lo(i, g.nx) * (i > 0 ? W[l - 1] : 0.f);
+    a7[l] = mul_hi(i, g.nx) * W[l];
+    a6[l] = mul_lo(j, g.ny) * (j > g.jlo() ? N[l - g.pitch] : 0.f);
+    a8[l] = mul_hi(j, g.ny) * N[l];
 }
 
 // dst(pitched rows [ja,jb)) = scale * src(dense, row 0 == ja)
@@ -325,11 +391,11 @@ static int pass1_rows_per_task(int nstrips, int nrows, int sm_count)
     return (int)rs;
 }
 
-void launch_pcg_pass1(const PcgBuffers& b, const Geom& g, int ja, int jb, int first, int cur, int store_halo,
+void launch_pcg_pass1(const PcgBuffers& b, const Geom& g, int ja, int jb, int ki, int store_halo,
                       int sm_count, cudaStream_t st)
 {
     P1Args a;
-    a.b = b; a.g = g; a.ja = ja; a.jb = jb; a.cur = cur; a.store_halo = store_halo;
+    a.b = b; a.g = g; a.ja = ja; a.jb = jb; a.cur = ki & 1; a.store_halo = store_halo;
     a.nstrips = (g.nx + 127) / 128;
     a.rs = pass1_rows_per_task(a.nstrips, jb - ja, sm_count);
     a.nsegs = (jb - ja + a.rs - 1) / a.rs;
@@ -338,31 +404,36 @@ void launch_pcg_pass1(const PcgBuffers& b, const Geom& g, int ja, int jb, int fi
     const int cap = sm_count * 16;
     if (grid > cap) grid = cap;
     if (grid > b.max_partial_blocks) grid = b.max_partial_blocks;
-    if (first) k_pcg_pass1<true><<<grid, 256, 0, st>>>(a);
-    else       k_pcg_pass1<false><<<grid, 256, 0, st>>>(a);
+    if (ki == 0)      k_pcg_pass1<XM_NONE><<<grid, 256, 0, st>>>(a);
+    else if (ki == 1) k_pcg_pass1<XM_INIT><<<grid, 256, 0, st>>>(a);
+    else              k_pcg_pass1<XM_ACC><<<grid, 256, 0, st>>>(a);
 }
 
-void launch_pcg_pass2(const PcgBuffers& b, const Geom& g, int ja, int jb, int first, int cur, int sm_count,
-                      cudaStream_t st)
+void launch_pcg_pass2(const PcgBuffers& b, const Geom& g, int ja, int jb, int sm_count, cudaStream_t st)
 {
     P2Args a;
-    a.b = b; a.g = g; a.ja = ja; a.jb = jb; a.cur = cur;
+    a.b = b; a.g = g; a.ja = ja; a.jb = jb;
     const long long nunits = (long long)(jb - ja) * (g.pitch >> 2);
     long long grid = (nunits + 255) / 256;
     const int cap = sm_count * 16;
     if (grid > cap) grid = cap;
     if (grid > b.max_partial_blocks) grid = b.max_partial_blocks;
-    if (first) k_pcg_pass2<true><<<(int)grid, 256, 0, st>>>(a);
-    else       k_pcg_pass2<false><<<(int)grid, 256, 0, st>>>(a);
+    k_pcg_pass2<<<(int)grid, 256, 0, st>>>(a);
 }
 
-void launch_update_uv(float* u, float* v, const float* xu, const float* xv, const Geom& g, int ja, int jb,
-                      const PcgScalars* s, int* its_out, int sm_count, cudaStream_t st)
+void launch_update_uv(float* u, float* v, const PcgBuffers& b, const Geom& g, int ja, int jb,
+                      int* its_out, int sm_count, cudaStream_t st)
 {
     const long long nunits = (long long)(jb - ja) * (g.pitch >> 2);
     long long grid = (nunits + 255) / 256;
     if (grid > sm_count * 16) grid = sm_count * 16;
-    k_update_uv<<<(int)grid, 256, 0, st>>>(u, v, xu, xv, g, ja, jb, s, its_out);
+    k_update_uv<<<(int)grid, 256, 0, st>>>(u, v, b, g, ja, jb, its_out);
+}
+
+void launch_expand_coef(const PcgBuffers& b, const Geom& g, float* a5, float* a6, float* a7, float* a8, cudaStream_t st)
+{
+    dim3 grid((g.nx + 255) / 256, g.ny);
+    k_expand_coef<<<grid, 256, 0, st>>>(b, g, a5, a6, a7, a8);
 }
 
 void launch_scale_copy(const float* src, float* dst, const Geom& g, int ja, int jb, float scale, cudaStream_t st)

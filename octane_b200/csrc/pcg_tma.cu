@@ -14,10 +14,11 @@
 // + 1 producer warp.  A task is a strip x row segment; tasks are dealt
 // round-robin to the persistent CTAs.  Stage layout for one row of a strip that
 // starts at column i0 (SW = strip width, multiple of 32):
-//   RU RV PU PV A1 A4 : SW+8 floats each, columns i0-4 .. i0+SW+3 (halo for the i-1/i+1 taps)
-//   A2 A5 A6 A7 A8    : SW floats each
-// Replaces jMatXVec/multiply_row + the p update of
-// src/oct_variational_optical_flow.cu:112-139,1138-1146,1161 (reference tree).
+//   RU RV PU PV A1 A4 W : SW+8 floats each, columns i0-4 .. i0+SW+3 (halo for the i-1/i+1 taps)
+//   A2 N XU XV          : SW floats each
+// W, A2, XU, XV are fetched for the task's own rows only, N also for the row above them.
+// Replaces jMatXVec/multiply_row + the p and x updates of
+// src/oct_variational_optical_flow.cu:112-139,1138-1146,1161,1172 (reference tree).
 #include "kernels.cuh"
 
 namespace octane {
@@ -28,7 +29,9 @@ constexpr int SWMAX = 1024;                 // pixels per strip (256 consumer th
 constexpr int HALO = 4;                     // floats of left halo (keeps 16-byte alignment)
 constexpr int NSTAGE = 4;
 constexpr int HA = SWMAX + 2 * HALO;        // floats per halo array
-constexpr int STAGE_FLOATS = 6 * HA + 5 * SWMAX;
+constexpr int NHALO = 7, NCENTRE = 4;
+constexpr int STAGE_FLOATS = NHALO * HA + NCENTRE * SWMAX;
+enum { XM_NONE = 0, XM_INIT = 1, XM_ACC = 2 };   // as in pcg.cu
 constexpr int CONSUMERS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,10 +87,17 @@ struct PRowT {
     float eu_l, ev_l, eu_r, ev_r;     // p of the pixels just left / right of the WARP's 128 pixels
 };
 
-// p_new of one staged row for this thread's 4 pixels (+ the warp-edge pixels in lanes 0 / 31)
-template <bool FIRST>
-__device__ __forceinline__ PRowT p_from_stage(const float* st, int i0s, int tcol, int nx, int lane, float beta)
+__device__ __forceinline__ float mul_lo(int i, int n) { return i == 0 ? 0.f : (i == n - 1 ? 2.f : 1.f); }
+__device__ __forceinline__ float mul_hi(int i, int n) { return i == n - 1 ? 0.f : (i == 0 ? 2.f : 1.f); }
+
+// p_new of one staged row for this thread's 4 pixels (+ the warp-edge pixels in lanes 0 / 31);
+// when `xdst` is set (the row is one of the task's own), also the previous iteration's pending
+// x += alpha_prev p_old (:1172), written straight to global memory.
+template <int XM>
+__device__ __forceinline__ PRowT p_from_stage(const float* st, int i0s, int tcol, int nx, int lane, float beta,
+                                              float alpha_prev, float* xu_dst, float* xv_dst)
 {
+    constexpr bool FIRST = (XM == XM_NONE);
     // tcol = 4*tid: this thread's first pixel inside the strip; halo arrays are shifted by HALO
     const float* RU = st;
     const float* RV = st + HA;
@@ -104,6 +114,25 @@ __device__ __forceinline__ PRowT p_from_stage(const float* st, int i0s, int tcol
     o.a4 = lds4(A4 + c);
     float4 po_u = make_float4(0.f, 0.f, 0.f, 0.f), po_v = po_u;
     if (!FIRST) { po_u = lds4(PU + c); po_v = lds4(PV + c); }
+    if (!FIRST && xu_dst) {
+        float4 x_u = make_float4(0.f, 0.f, 0.f, 0.f), x_v = x_u;
+        if (XM == XM_ACC) {
+            const float* XU = st + NHALO * HA + 2 * SWMAX;
+            x_u = lds4(XU + tcol);
+            x_v = lds4(XU + SWMAX + tcol);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0s + tcol + k < nx) {
+                el(x_u, k) = fmaf(alpha_prev, el(po_u, k), el(x_u, k));
+                el(x_v, k) = fmaf(alpha_prev, el(po_v, k), el(x_v, k));
+            } else {
+                el(x_u, k) = 0.f; el(x_v, k) = 0.f;
+            }
+        }
+        stg4(xu_dst, x_u);
+        stg4(xv_dst, x_v);
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         if (i0s + tcol + k < nx) {
@@ -127,9 +156,10 @@ __device__ __forceinline__ PRowT p_from_stage(const float* st, int i0s, int tcol
     return o;
 }
 
-template <bool FIRST>
+template <int XM>
 __global__ void __launch_bounds__(CONSUMERS + 32, 1) k_pcg_pass1_tma(TArgs a)
 {
+    constexpr bool FIRST = (XM == XM_NONE);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red[32];
     __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE];
@@ -150,8 +180,8 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 1) k_pcg_pass1_tma(TArgs a)
     if (tid >= CONSUMERS) {
         // ---------------- producer: one thread walks the same (task, row) sequence ----------------
         if (tid == CONSUMERS) {
-            const float* src_h[6] = { a.b.ru, a.b.rv, a.b.pu[a.cur], a.b.pv[a.cur], a.b.coef[0], a.b.coef[2] };
-            const float* src_c[5] = { a.b.coef[1], a.b.coef[3], a.b.coef[4], a.b.coef[5], a.b.coef[6] };
+            const float* src_h[NHALO] = { a.b.ru, a.b.rv, a.b.pu[a.cur], a.b.pv[a.cur], a.b.coef[C_A1], a.b.coef[C_A4],
+                                          a.b.coef[C_W] };
             uint32_t it = 0;
             for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
                 const int seg = t / a.nstrips, strip = t - seg * a.nstrips;
@@ -167,18 +197,23 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 1) k_pcg_pass1_tma(TArgs a)
                     mbar_wait(&empty_bar[stg], par ^ 1u);
                     float* st = stages + (size_t)stg * STAGE_FLOATS;
                     const bool centre = jr >= j_a && jr < j_b;
-                    const int nh = FIRST ? 4 : 6;
-                    mbar_expect_tx(&full_bar[stg], (uint32_t)nh * hb + (centre ? 5u * cb : 0u));
+                    const bool need_n = jr < j_b;                    // own rows and the row above them
+                    const uint32_t nh = (FIRST ? 4u : 6u) + (centre ? 1u : 0u);
+                    const uint32_t ncb = (centre ? 1u : 0u) + (need_n ? 1u : 0u) + ((centre && XM == XM_ACC) ? 2u : 0u);
+                    mbar_expect_tx(&full_bar[stg], nh * hb + ncb * cb);
                     const size_t row = g.at(0, jr);
 #pragma unroll
-                    for (int q = 0; q < 6; q++) {
+                    for (int q = 0; q < NHALO; q++) {
                         if (FIRST && (q == 2 || q == 3)) continue;
+                        if (q == 6 && !centre) continue;
                         bulk_g2s(st + q * HA + (h0 - (i0s - HALO)), src_h[q] + row + h0, hb, &full_bar[stg]);
                     }
-                    if (centre) {
-#pragma unroll
-                        for (int q = 0; q < 5; q++)
-                            bulk_g2s(st + 6 * HA + q * SWMAX, src_c[q] + row + i0s, cb, &full_bar[stg]);
+                    float* cst = st + NHALO * HA;
+                    if (centre) bulk_g2s(cst, a.b.coef[C_A2] + row + i0s, cb, &full_bar[stg]);
+                    if (need_n) bulk_g2s(cst + SWMAX, a.b.coef[C_N] + row + i0s, cb, &full_bar[stg]);
+                    if (centre && XM == XM_ACC) {
+                        bulk_g2s(cst + 2 * SWMAX, a.b.xu + row + i0s, cb, &full_bar[stg]);
+                        bulk_g2s(cst + 3 * SWMAX, a.b.xv + row + i0s, cb, &full_bar[stg]);
                     }
                 }
             }
@@ -186,6 +221,7 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 1) k_pcg_pass1_tma(TArgs a)
     } else {
         // ---------------- consumers -------------------------------------------------------------
         const float beta = FIRST ? 0.f : s->rz / s->rz_old;           // Bk, :1144
+        const float alpha_prev = FIRST ? 0.f : s->alpha;
         const int lane = tid & 31;
         const int tcol = tid * 4;
         float* pu_new = a.b.pu[a.cur ^ 1];
@@ -201,15 +237,23 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 1) k_pcg_pass1_tma(TArgs a)
             up.pu = up.pv = up.a1 = up.a4 = make_float4(0.f, 0.f, 0.f, 0.f);
             up.eu_l = up.ev_l = up.eu_r = up.ev_r = 0.f;
             ce = up;
+            float4 n_up = make_float4(0.f, 0.f, 0.f, 0.f);       // N of the row above the centre row
+            float4 n_ce = n_up;                                  // N of the row that is about to become the centre
             int prev_stage = -1;                       // stage holding the centre row's coefficients
             for (int jr = j_a - 1; jr <= j_b; jr++) {
                 int stg = -1;
+                float4 n_dn = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (jr >= 0 && jr < g.ny) {
                     stg = it % NSTAGE;
                     mbar_wait(&full_bar[stg], (it / NSTAGE) & 1u);
                     it++;
-                    dn = p_from_stage<FIRST>(stages + (size_t)stg * STAGE_FLOATS, i0s, tcol, g.nx, lane, beta);
+                    const float* st = stages + (size_t)stg * STAGE_FLOATS;
+                    const bool own = active && jr >= j_a && jr < j_b;
+                    const size_t xoff = own ? g.at(i0, jr) : 0;
+                    dn = p_from_stage<XM>(st, i0s, tcol, g.nx, lane, beta, alpha_prev,
+                                          own ? a.b.xu + xoff : nullptr, own ? a.b.xv + xoff : nullptr);
                     if (!active) { dn.pu = dn.pv = make_float4(0.f, 0.f, 0.f, 0.f); }
+                    if (active && jr < j_b) n_dn = lds4(st + NHALO * HA + SWMAX + tcol);
                 } else {
                     dn.pu = dn.pv = dn.a1 = dn.a4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     dn.eu_l = dn.ev_l = dn.eu_r = dn.ev_r = 0.f;
@@ -221,29 +265,35 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 1) k_pcg_pass1_tma(TArgs a)
                     if (lane == 0) { lu = ce.eu_l; lv = ce.ev_l; }
                     if (lane == 31) { ru_ = ce.eu_r; rv_ = ce.ev_r; }
                     if (active) {
-                        const float* cst = stages + (size_t)prev_stage * STAGE_FLOATS + 6 * HA + tcol;
-                        const float4 a2 = lds4(cst), a5 = lds4(cst + SWMAX), a6 = lds4(cst + 2 * SWMAX),
-                                     a7 = lds4(cst + 3 * SWMAX), a8 = lds4(cst + 4 * SWMAX);
+                        const float* pst = stages + (size_t)prev_stage * STAGE_FLOATS;
+                        const float4 a2 = lds4(pst + NHALO * HA + tcol);
+                        const float* Wrow = pst + 6 * HA + HALO + tcol;
+                        const float4 w = lds4(Wrow);
+                        const float wl = (i0 > 0) ? Wrow[-1] : 0.f;     // column i0-1 (never staged at the image edge)
+                        const float m6 = mul_lo(jc, g.ny), m8 = mul_hi(jc, g.ny);
                         float4 qu, qv;
                         float part = 0.f;
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             const float pl_u = (k == 0) ? lu : el(ce.pu, k - 1), pl_v = (k == 0) ? lv : el(ce.pv, k - 1);
                             const float pr_u = (k == 3) ? ru_ : el(ce.pu, k + 1), pr_v = (k == 3) ? rv_ : el(ce.pv, k + 1);
+                            const float a5 = mul_lo(i0 + k, g.nx) * ((k == 0) ? wl : el(w, k - 1));
+                            const float a7 = mul_hi(i0 + k, g.nx) * el(w, k);
+                            const float a6 = m6 * el(n_up, k), a8 = m8 * el(n_ce, k);
                             float su = 0.f;                       // multiply_row order: [j-1] [i-1] a1 a2 [i+1] [j+1]
-                            su = fmaf(el(a6, k), el(up.pu, k), su);
-                            su = fmaf(el(a5, k), pl_u, su);
+                            su = fmaf(a6, el(up.pu, k), su);
+                            su = fmaf(a5, pl_u, su);
                             su = fmaf(el(ce.a1, k), el(ce.pu, k), su);
                             su = fmaf(el(a2, k), el(ce.pv, k), su);
-                            su = fmaf(el(a7, k), pr_u, su);
-                            su = fmaf(el(a8, k), el(dn.pu, k), su);
+                            su = fmaf(a7, pr_u, su);
+                            su = fmaf(a8, el(dn.pu, k), su);
                             float sv = 0.f;
-                            sv = fmaf(el(a6, k), el(up.pv, k), sv);
-                            sv = fmaf(el(a5, k), pl_v, sv);
+                            sv = fmaf(a6, el(up.pv, k), sv);
+                            sv = fmaf(a5, pl_v, sv);
                             sv = fmaf(el(a2, k), el(ce.pu, k), sv);
                             sv = fmaf(el(ce.a4, k), el(ce.pv, k), sv);
-                            sv = fmaf(el(a7, k), pr_v, sv);
-                            sv = fmaf(el(a8, k), el(dn.pv, k), sv);
+                            sv = fmaf(a7, pr_v, sv);
+                            sv = fmaf(a8, el(dn.pv, k), sv);
                             const bool in = i0 + k < g.nx;
                             el(qu, k) = in ? su : 0.f;
                             el(qv, k) = in ? sv : 0.f;
@@ -270,6 +320,8 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 1) k_pcg_pass1_tma(TArgs a)
                 prev_stage = stg;
                 up = ce;
                 ce = dn;
+                n_up = n_ce;
+                n_ce = n_dn;
             }
             // last staged row of the task (row j_b, or none when j_b == ny)
             if (a.store_halo && active && j_b == a.jb && j_b < g.ny) {
@@ -300,11 +352,11 @@ bool pcg_pass1_tma_usable(const Geom& g, int nrows)
     return g.nx >= 512 && nrows >= 64 && (g.pitch % 32) == 0;
 }
 
-void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, int first, int cur, int store_halo,
+void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, int ki, int store_halo,
                           int sm_count, cudaStream_t st)
 {
     TArgs a;
-    a.b = b; a.g = g; a.ja = ja; a.jb = jb; a.cur = cur; a.store_halo = store_halo;
+    a.b = b; a.g = g; a.ja = ja; a.jb = jb; a.cur = ki & 1; a.store_halo = store_halo;
     a.nstrips = (g.nx + SWMAX - 1) / SWMAX;
     a.sw = round_up((g.nx + a.nstrips - 1) / a.nstrips, 32);
     if (a.sw > SWMAX) a.sw = SWMAX;
@@ -328,12 +380,14 @@ void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, in
     const size_t smem = (size_t)NSTAGE * STAGE_FLOATS * sizeof(float);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_pcg_pass1_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pcg_pass1_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    if (first) k_pcg_pass1_tma<true><<<grid, CONSUMERS + 32, smem, st>>>(a);
-    else       k_pcg_pass1_tma<false><<<grid, CONSUMERS + 32, smem, st>>>(a);
+    if (ki == 0)      k_pcg_pass1_tma<XM_NONE><<<grid, CONSUMERS + 32, smem, st>>>(a);
+    else if (ki == 1) k_pcg_pass1_tma<XM_INIT><<<grid, CONSUMERS + 32, smem, st>>>(a);
+    else              k_pcg_pass1_tma<XM_ACC><<<grid, CONSUMERS + 32, smem, st>>>(a);
 }
 
 }  // namespace octane

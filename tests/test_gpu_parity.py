@@ -203,7 +203,11 @@ def test_stage_build_and_pcg(ctx, oracle, gnc, nc):
     # x ~ 0 (psi up to 1000): there a 1-ulp change of x moves the coefficient by up to ~0.2 %
     err = np.abs(gc - coef) / scale
     assert np.quantile(err, 0.999) < 2e-5 and err.max() < 5e-3
-    assert np.abs(gbu - bu).max() < 2e-5 * max(1.0, np.abs(bu).max()) and np.abs(gbv - bv).max() < 2e-5 * max(1.0, np.abs(bv).max())
+    # the rhs holds sum_k psi_k u_k - (sum_k psi_k) u with psi up to 1000: its absolute rounding noise
+    # scales with the diagonal, not with |b|
+    for got, want in ((gbu, bu), (gbv, bv)):
+        e = np.abs(got - want)
+        assert np.quantile(e, 0.999) < 1e-4 * max(1.0, np.abs(want).max()) and e.max() < 2e-6 * scale[0].max()
     # boundary-merged entries: absent neighbours are exactly zero
     assert np.all(gc[3][:, 0] == 0) and np.all(gc[5][:, -1] == 0) and np.all(gc[4][0, :] == 0) and np.all(gc[6][-1, :] == 0)
     # PCG on the oracle's system: same iterate after the same number of iterations
@@ -226,7 +230,10 @@ def test_pcg_stop_rule_and_zero_rhs(ctx):
     coef[0] = 9; coef[2] = 9
     for k in (3, 4, 5, 6):
         coef[k] = -1
+    # mirror-merged edges as the build produces them (:929-1077): the absent neighbour's entry is
+    # zero and its weight is added to the opposite one
     coef[3][:, 0] = 0; coef[5][:, -1] = 0; coef[4][0, :] = 0; coef[6][-1, :] = 0
+    coef[3][:, -1] = -2; coef[5][:, 0] = -2; coef[4][-1, :] = -2; coef[6][0, :] = -2
     z = np.zeros((ny, nx), np.float32)
     dxu, dxv = torch.ones((ny, nx), device="cuda"), torch.ones((ny, nx), device="cuda")
     assert ctx.stage_pcg(dev(coef), dev(z), dev(z), nx, ny, 30, 1e-8, dxu, dxv) == 0     # ||b||^2 <= tol: no iteration
