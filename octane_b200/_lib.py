@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "liboctane_b200.so")
+# OCTANE_B200_LIB: load another build of the same C ABI (A/B comparisons of kernel revisions)
+LIB_PATH = os.environ.get("OCTANE_B200_LIB") or os.path.join(HERE, "lib", "liboctane_b200.so")
 
 OCTANE_MAX_SOLVES = 256
 

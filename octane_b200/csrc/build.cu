@@ -7,6 +7,8 @@
 // pixel (the 2x2 diagonal block and the couplings to i+1 and j+1; the other two
 // couplings are their neighbours' by symmetry), the right-hand side, and seeds
 // the PCG scalars (r0 = b because x0 = 0).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace octane {
@@ -15,13 +17,34 @@ namespace octane {
 
 __device__ __forceinline__ float jsq(float x) { return x * x; }
 
-// :72-108
+// ---- exact shortcuts for the reference's mixed-precision expressions ----------------------
+// The reference's promotion rules force fp64 divisions where the operands are floats; each
+// helper below returns the SAME float, bit for bit, with less work (CPU proof by enumeration:
+// tests/test_abi_host.py::test_exact_division_shortcuts).
+
+// float(1. / double(s)) for a float s.  1/s cannot fall within 2^-49 (relative) of a float
+// rounding boundary unless it is exactly on one (s times a 25-bit midpoint would have to be
+// within 1 of a power of two), so rounding to double first never changes the float result:
+// it is the correctly rounded single-precision reciprocal.
+__device__ __forceinline__ float recip_f(float s) { return __frcp_rn(s); }
+
+// double(x) / a for a float x and a double constant a with y = RN(1/a): one Markstein
+// correction step after the multiply gives the correctly rounded quotient.
+__device__ __forceinline__ double div_const(float x, double a, double y)
+{
+    const double xd = (double)x;
+    const double q = xd * y;
+    const double r = fma(-q, a, xd);
+    return fma(r, y, q);
+}
+
+// oct_PSI_smooth_cu, :72-88: float(1. / double(sqrtf(float(double(x) + 1E-6))))
 __device__ __forceinline__ float psi_smooth(float x)
 {
-    float answer;
-    answer = 1. / (sqrtf((x + 1E-6)));
-    return answer;
+    const float s = (float)(x + 1E-6);
+    return recip_f(sqrtf(s));
 }
+// oct_PSI_data_cu, :90-108: float(1. / sqrt(double(x) + 1E-6))
 __device__ __forceinline__ float psi_data(float x)
 {
     float answer;
@@ -34,50 +57,68 @@ __device__ __forceinline__ float binterp(float p1, float p2, float p3, float p4,
 {
     return p3 * ((p1)*f11 + (p2)*f21) + p4 * ((p1)*f12 + (p2)*f22);
 }
+__device__ __forceinline__ float gather(const float* __restrict__ q, int pitch, float p1, float p2, float p3, float p4)
+{
+    return binterp(p1, p2, p3, p4, __ldg(q), __ldg(q + 1), __ldg(q + pitch), __ldg(q + pitch + 1));
+}
 
-__global__ void __launch_bounds__(256)
+// GNC stage of a launch (:604-606): al1 = 1 - 0.5*gnc.  Every coefficient is
+// al1*(quadratic term) + (1-al1)*(robust term) evaluated in double and cast to float; with
+// al1 == 1 the robust term is multiplied by zero and with al1 == 0 the quadratic one is, so
+// those launches skip it (x*1 + y*0 == x exactly for finite y; the robust weights are finite
+// because psi(x) = 1/sqrt(x + 1e-6) with x >= 0).
+enum { GNC_QUADRATIC = 0, GNC_BLEND = 1, GNC_ROBUST = 2 };
+
+template <int MODE, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 k_build(LevelFields f, PcgBuffers b, Geom g, int ja, int jb, int da, int db, BuildParams bp, int halo_check)
 {
+    constexpr bool ROBUST = (MODE != GNC_QUADRATIC);   // robust terms needed
+    constexpr bool QUAD = (MODE != GNC_ROBUST);        // quadratic terms needed
     __shared__ double red[2 * 32];
     const int ii = blockIdx.x * 32 + threadIdx.x;
-    const int xi = g.nx, yi = g.ny;
+    const int xi = g.nx, yi = g.ny, pitch = g.pitch;
+    const double alpha = bp.alpha, ralpha = bp.ralpha, lambdadalpha = bp.lambdadalpha, al1 = bp.al1;
+    const float lambdac = bp.lambdac;
     double acc[2] = { 0.0, 0.0 };
 
     // a block covers 32 columns x BUILD_ROWS rows, 8 rows at a time
     for (int jt = 0; jt < BUILD_ROWS; jt += 8) {
     const int jj = ja + blockIdx.y * BUILD_ROWS + jt + threadIdx.y;
     if (ii < xi && jj < jb) {
-        const double alpha = bp.alpha, lambdadalpha = bp.lambdadalpha, al1 = bp.al1;
-        const float lambdac = bp.lambdac;
         // mirror-without-repeat neighbours (:629-652)
         const int im = (ii == 0) ? ii + 1 : ii - 1;
         const int ip = (ii == xi - 1) ? ii - 1 : ii + 1;
         const int jm = (jj == 0) ? jj + 1 : jj - 1;
         const int jp = (jj == yi - 1) ? jj - 1 : jj + 1;
-        const float* u = f.u;
-        const float* v = f.v;
-        const size_t rm = g.at(0, jm), r0 = g.at(0, jj), rp = g.at(0, jp);
-        float up1p0 = u[r0 + ip], up0p0 = u[r0 + ii], up1p1 = u[rp + ip], up1m1 = u[rm + ip];
-        float up0p1 = u[rp + ii], up0m1 = u[rm + ii], um1p1 = u[rp + im], um1p0 = u[r0 + im], um1m1 = u[rm + im];
-        float vp1p0 = v[r0 + ip], vp0p0 = v[r0 + ii], vp1p1 = v[rp + ip], vp1m1 = v[rm + ip];
-        float vp0p1 = v[rp + ii], vp0m1 = v[rm + ii], vm1p1 = v[rp + im], vm1p0 = v[r0 + im], vm1m1 = v[rm + im];
+        const size_t r0 = g.at(0, jj);
+        const float* u0 = f.u + r0;
+        const float* v0 = f.v + r0;
+        const int dm = (jm - jj) * pitch, dp = (jp - jj) * pitch;     // +-pitch
+        const float up0p0 = u0[ii], up1p0 = u0[ip], um1p0 = u0[im], up0p1 = u0[dp + ii], up0m1 = u0[dm + ii];
+        const float vp0p0 = v0[ii], vp1p0 = v0[ip], vm1p0 = v0[im], vp0p1 = v0[dp + ii], vp0m1 = v0[dm + ii];
 
-        // :680-683
-        float Uip1 = jsq(up1p0 - up0p0) + jsq(0.25 * ((up1p1 - up1m1) + (up0p1 - up0m1))) + jsq(vp1p0 - vp0p0) + jsq(0.25 * ((vp1p1 - vp1m1) + (vp0p1 - vp0m1)));
-        float Uim1 = jsq(up0p0 - um1p0) + jsq(0.25 * ((um1p1 - um1m1) + (up0p1 - up0m1))) + jsq(vp0p0 - vm1p0) + jsq(0.25 * ((vm1p1 - vm1m1) + (vp0p1 - vp0m1)));
-        float Ujp1 = jsq(up0p1 - up0p0) + jsq(0.25 * ((up1p1 - um1p1) + (up1p0 - um1p0))) + jsq(vp0p1 - vp0p0) + jsq(0.25 * ((vp1p1 - vm1p1) + (vp1p0 - vm1p0)));
-        float Ujm1 = jsq(up0p0 - up0m1) + jsq(0.25 * ((up1m1 - um1m1) + (up1p0 - um1p0))) + jsq(vp0p0 - vp0m1) + jsq(0.25 * ((vp1m1 - vm1m1) + (vp1p0 - vm1p0)));
-        // :714-724
-        float psis1 = psi_smooth(Uim1);
-        float psis2 = psi_smooth(Ujm1);
-        float psis3 = psi_smooth(Uip1);
-        float psis4 = psi_smooth(Ujp1);
-        float psistot = psis1 + psis2 + psis3 + psis4;
-        float psistotq = 4.;
-        float psisnmiu = psis1 * (um1p0) + psis2 * (up0m1) + psis3 * (up1p0) + psis4 * (up0p1);
-        float psisnmiv = psis1 * (vm1p0) + psis2 * (vp0m1) + psis3 * (vp1p0) + psis4 * (vp0p1);
-        float psisnmiuq = um1p0 + up0m1 + up1p0 + up0p1;
-        float psisnmivq = vm1p0 + vp0m1 + vp1p0 + vp0p1;
+        float psis3 = 0.f, psis4 = 0.f, psistot = 0.f, psisnmiu = 0.f, psisnmiv = 0.f;
+        if (ROBUST) {
+            const float up1p1 = u0[dp + ip], up1m1 = u0[dm + ip], um1p1 = u0[dp + im], um1m1 = u0[dm + im];
+            const float vp1p1 = v0[dp + ip], vp1m1 = v0[dm + ip], vm1p1 = v0[dp + im], vm1m1 = v0[dm + im];
+            // :680-683 (0.25 * x is exact in either precision, so the reference's detour through double is dropped)
+            float Uip1 = jsq(up1p0 - up0p0) + jsq(0.25f * ((up1p1 - up1m1) + (up0p1 - up0m1))) + jsq(vp1p0 - vp0p0) + jsq(0.25f * ((vp1p1 - vp1m1) + (vp0p1 - vp0m1)));
+            float Uim1 = jsq(up0p0 - um1p0) + jsq(0.25f * ((um1p1 - um1m1) + (up0p1 - up0m1))) + jsq(vp0p0 - vm1p0) + jsq(0.25f * ((vm1p1 - vm1m1) + (vp0p1 - vp0m1)));
+            float Ujp1 = jsq(up0p1 - up0p0) + jsq(0.25f * ((up1p1 - um1p1) + (up1p0 - um1p0))) + jsq(vp0p1 - vp0p0) + jsq(0.25f * ((vp1p1 - vm1p1) + (vp1p0 - vm1p0)));
+            float Ujm1 = jsq(up0p0 - up0m1) + jsq(0.25f * ((up1m1 - um1m1) + (up1p0 - um1p0))) + jsq(vp0p0 - vp0m1) + jsq(0.25f * ((vp1m1 - vm1m1) + (vp1p0 - vm1p0)));
+            // :714-724
+            float psis1 = psi_smooth(Uim1);
+            float psis2 = psi_smooth(Ujm1);
+            psis3 = psi_smooth(Uip1);
+            psis4 = psi_smooth(Ujp1);
+            psistot = psis1 + psis2 + psis3 + psis4;
+            psisnmiu = psis1 * (um1p0) + psis2 * (up0m1) + psis3 * (up1p0) + psis4 * (up0p1);
+            psisnmiv = psis1 * (vm1p0) + psis2 * (vp0m1) + psis3 * (vp1p0) + psis4 * (vp0p1);
+        }
+        const float psistotq = 4.;
+        const float psisnmiuq = um1p0 + up0m1 + up1p0 + up0p1;
+        const float psisnmivq = vm1p0 + vp0m1 + vp1p0 + vp0p1;
 
         float vr1 = 0, vr2 = 0, vr4 = 0, vr5 = 0, vr6 = 0, intcomp = 0;
         float vr12 = 0, vr22 = 0, vr42 = 0, vr52 = 0, vr62 = 0, intcomp2 = 0;
@@ -100,23 +141,23 @@ k_build(LevelFields f, PcgBuffers b, Geom g, int ja, int jb, int da, int db, Bui
                 jv1 = min(max(jv1, g.jlo()), g.jhi() - 2);
             }
         }
-        const size_t c1 = g.at(iv1, jv1), c2 = c1 + 1, c3 = c1 + g.pitch, c4 = c3 + 1;
+        const size_t c1 = g.at(iv1, jv1);
         const size_t l = r0 + ii;
-        // bilinear weights, :57-65 (x2-x1 == y2-y1 == 1)
+        // bilinear weights, :57-65; x2-x1 == y2-y1 == 1.0f exactly, so the divisions are dropped
         const float x1 = iv1, x2 = iv1 + 1, y1 = jv1, y2 = jv1 + 1;
-        const float p1 = (x2 - iv) / (x2 - x1);
-        const float p2 = (iv - x1) / (x2 - x1);
-        const float p3 = ((y2 - jv) / (y2 - y1));
-        const float p4 = ((jv - y1) / (y2 - y1));
+        const float p1 = x2 - iv;
+        const float p2 = iv - x1;
+        const float p3 = y2 - jv;
+        const float p4 = jv - y1;
         for (int c = 0; c < bp.nchan; c++) {
             const size_t off = (size_t)c * g.plane;
-            const float* q;
-            q = f.g2 + off;   float g2 = binterp(p1, p2, p3, p4, __ldg(q + c1), __ldg(q + c2), __ldg(q + c3), __ldg(q + c4));
-            q = f.g2x + off;  float Ix = binterp(p1, p2, p3, p4, __ldg(q + c1), __ldg(q + c2), __ldg(q + c3), __ldg(q + c4));
-            q = f.g2y + off;  float Iy = binterp(p1, p2, p3, p4, __ldg(q + c1), __ldg(q + c2), __ldg(q + c3), __ldg(q + c4));
-            q = f.g2xx + off; float Ixx = binterp(p1, p2, p3, p4, __ldg(q + c1), __ldg(q + c2), __ldg(q + c3), __ldg(q + c4));
-            q = f.g2xy + off; float Ixy = binterp(p1, p2, p3, p4, __ldg(q + c1), __ldg(q + c2), __ldg(q + c3), __ldg(q + c4));
-            q = f.g2yy + off; float Iyy = binterp(p1, p2, p3, p4, __ldg(q + c1), __ldg(q + c2), __ldg(q + c3), __ldg(q + c4));
+            const size_t oc = off + c1;
+            float g2 = gather(f.g2 + oc, pitch, p1, p2, p3, p4);
+            float Ix = gather(f.g2x + oc, pitch, p1, p2, p3, p4);
+            float Iy = gather(f.g2y + oc, pitch, p1, p2, p3, p4);
+            float Ixx = gather(f.g2xx + oc, pitch, p1, p2, p3, p4);
+            float Ixy = gather(f.g2xy + oc, pitch, p1, p2, p3, p4);
+            float Iyy = gather(f.g2yy + oc, pitch, p1, p2, p3, p4);
             // derivative zeroing where the warp was clamped, :768-779
             if (bc2) { Ix = 0.; Ixx = 0.; Ixy = 0.; }
             if (bc3) { Iy = 0.; Ixy = 0.; Iyy = 0.; }
@@ -137,8 +178,10 @@ k_build(LevelFields f, PcgBuffers b, Geom g, int ja, int jb, int da, int db, Bui
             } else {
                 na = 1.; nb = 1.; nc = 1.;
             }
-            intcomp += na * It * It;
-            intcomp2 += (nb * Ixt * Ixt + nc * Iyt * Iyt);
+            if (ROBUST) {
+                intcomp += na * It * It;
+                intcomp2 += (nb * Ixt * Ixt + nc * Iyt * Iyt);
+            }
             vr1 += (na * IxIx);
             vr12 += (nb * IxxIxx + nc * IxyIxy);
             vr2 += na * Ix * Iy;
@@ -153,14 +196,46 @@ k_build(LevelFields f, PcgBuffers b, Geom g, int ja, int jb, int da, int db, Bui
             vr6 += natIt * Iy;
             vr62 += -(nbtIxt * Ixy + nctIyt * Iyy);
         }
-        // :831-864
-        float psid = psi_data(intcomp) / alpha;
-        float psid2 = lambdadalpha * psi_data(intcomp2);
-        float a1 = (float)((al1) * ((vr1) / alpha + lambdadalpha * (vr12) + lambdac + psistotq) + (1 - al1) * (psid * (vr1) + psid2 * vr12 + lambdac + psistot));
-        float a2 = (float)((al1) * ((vr2) / alpha + lambdadalpha * vr22) + (1 - al1) * (psid * (vr2) + psid2 * vr22));
-        float a4 = (float)((al1) * ((vr4) / alpha + lambdadalpha * vr42 + lambdac + psistotq) + (1 - al1) * (psid * (vr4) + psid2 * vr42 + lambdac + psistot));
-        float a7 = (float)(-1 * (al1 + (1 - al1) * (psis3)));
-        float a8 = (float)(-1 * (al1 + (1 - al1) * (psis4)));
+        // right-hand-side hint term, :1087-1092
+        const float uvt = f.uh ? __ldg(f.uh + l) : 0.f;
+        const float vvt = f.vh ? __ldg(f.vh + l) : 0.f;
+        const float val2u = lambdac * (up0p0 - uvt);
+        const float val2v = lambdac * (vp0p0 - vvt);
+        // :831-864.  Quadratic (q*) and robust (r*) halves of every entry, then the GNC blend.
+        double q1 = 0., q2 = 0., q4 = 0., qbu = 0., qbv = 0.;
+        float r1 = 0.f, r2 = 0.f, r4 = 0.f, rbu = 0.f, rbv = 0.f;
+        if (QUAD) {
+            q1 = div_const(vr1, alpha, ralpha) + lambdadalpha * (vr12) + lambdac + psistotq;
+            q2 = div_const(vr2, alpha, ralpha) + lambdadalpha * vr22;
+            q4 = div_const(vr4, alpha, ralpha) + lambdadalpha * vr42 + lambdac + psistotq;
+            qbu = div_const(vr5, alpha, ralpha) + lambdadalpha * vr52 - val2u + psisnmiuq - psistotq * up0p0;
+            qbv = div_const(vr6, alpha, ralpha) + lambdadalpha * vr62 - val2v + psisnmivq - psistotq * vp0p0;
+        }
+        if (ROBUST) {
+            float psid = div_const(psi_data(intcomp), alpha, ralpha);
+            float psid2 = lambdadalpha * psi_data(intcomp2);
+            r1 = psid * (vr1) + psid2 * vr12 + lambdac + psistot;
+            r2 = psid * (vr2) + psid2 * vr22;
+            r4 = psid * (vr4) + psid2 * vr42 + lambdac + psistot;
+            rbu = psid * (vr5) + psid2 * vr52 - val2u + psisnmiu - psistot * up0p0;
+            rbv = psid * (vr6) + psid2 * vr62 - val2v + psisnmiv - psistot * vp0p0;
+        }
+        float a1, a2, a4, a7, a8, bu, bv;
+        if (MODE == GNC_QUADRATIC) {
+            a1 = (float)q1; a2 = (float)q2; a4 = (float)q4; bu = (float)qbu; bv = (float)qbv;
+            a7 = -1.f; a8 = -1.f;
+        } else if (MODE == GNC_ROBUST) {
+            a1 = r1; a2 = r2; a4 = r4; bu = rbu; bv = rbv;
+            a7 = -psis3; a8 = -psis4;
+        } else {
+            a1 = (float)((al1) * (q1) + (1 - al1) * (r1));
+            a2 = (float)((al1) * (q2) + (1 - al1) * (r2));
+            a4 = (float)((al1) * (q4) + (1 - al1) * (r4));
+            a7 = (float)(-1 * (al1 + (1 - al1) * (psis3)));
+            a8 = (float)(-1 * (al1 + (1 - al1) * (psis4)));
+            bu = (float)(al1 * (qbu) + (1. - al1) * (rbu));
+            bv = (float)(al1 * (qbv) + (1 - al1) * (rbv));
+        }
         // Only the couplings to i+1 and j+1 are stored: a5(i,j) == a7(i-1,j) and
         // a6(i,j) == a8(i,j-1) bit for bit (same expression, two commuted additions), and at a
         // mirrored edge a5 == a7 (a6 == a8), so the boundary merging of :929-1077 -- the weight
@@ -171,20 +246,11 @@ k_build(LevelFields f, PcgBuffers b, Geom g, int ja, int jb, int da, int db, Bui
         b.coef[C_A4][l] = a4;
         b.coef[C_W][l] = a7;
         b.coef[C_N][l] = a8;
-        // right-hand side, :1087-1092
-        float uvt = f.uh ? __ldg(f.uh + l) : 0.f;
-        float vvt = f.vh ? __ldg(f.vh + l) : 0.f;
-        float val2 = lambdac * (up0p0 - uvt);
-        float bu = (float)(al1 * ((vr5) / alpha + lambdadalpha * vr52 - val2 + psisnmiuq - psistotq * up0p0) +
-                           (1. - al1) * (psid * (vr5) + psid2 * vr52 - val2 + psisnmiu - psistot * up0p0));
-        val2 = lambdac * (vp0p0 - vvt);
-        float bv = (float)(al1 * ((vr6) / alpha + lambdadalpha * vr62 - val2 + psisnmivq - psistotq * vp0p0) +
-                           (1 - al1) * (psid * (vr6) + psid2 * vr62 - val2 + psisnmiv - psistot * vp0p0));
         b.ru[l] = bu;
         b.rv[l] = bv;
         if (jj >= da && jj < db) {
             // residc = b.b (:1126); rkTzk = b.z with z = (1/M) b (:1115-1117,1157)
-            const float mu = 1. / a1, mv = 1. / a4;
+            const float mu = recip_f(a1), mv = recip_f(a4);
             const float zu = mu * bu, zv = mv * bv;
             acc[0] += (double)(bu * bu) + (double)(bv * bv);
             acc[1] += (double)(bu * zu) + (double)(bv * zv);
@@ -230,7 +296,17 @@ void launch_build(const LevelFields& f, const PcgBuffers& b, const Geom& g, int 
                   const BuildParams& bp, int halo_check, cudaStream_t st)
 {
     dim3 grid((g.nx + 31) / 32, (jb - ja + BUILD_ROWS - 1) / BUILD_ROWS), block(32, 8);
-    k_build<<<grid, block, 0, st>>>(f, b, g, ja, jb, da, db, bp, halo_check);
+    // developer switch: resident blocks per SM the register allocation aims at (2 -> 128 registers, no spills)
+    static const int occ = getenv("OCTANE_BUILD_OCC") ? atoi(getenv("OCTANE_BUILD_OCC")) : 3;
+#define LAUNCH_BUILD(MODE)                                                                              \
+    do {                                                                                                \
+        if (occ == 2) k_build<MODE, 2><<<grid, block, 0, st>>>(f, b, g, ja, jb, da, db, bp, halo_check); \
+        else          k_build<MODE, 3><<<grid, block, 0, st>>>(f, b, g, ja, jb, da, db, bp, halo_check); \
+    } while (0)
+    if (bp.al1 == 1.0)      LAUNCH_BUILD(GNC_QUADRATIC);
+    else if (bp.al1 == 0.0) LAUNCH_BUILD(GNC_ROBUST);
+    else                    LAUNCH_BUILD(GNC_BLEND);
+#undef LAUNCH_BUILD
     k_build_finish<<<1, 1024, 0, st>>>(b, grid.x * grid.y, bp.tol);
 }
 

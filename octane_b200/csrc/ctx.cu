@@ -470,7 +470,7 @@ int run_levels(octane_ctx* c)
         f.uh = (L.lambdac != 0.f) ? hu : nullptr;
         f.vh = (L.lambdac != 0.f) ? hv : nullptr;
         BuildParams bp;
-        bp.alpha = p.alpha; bp.lambdadalpha = p.lambda / p.alpha; bp.lambdac = L.lambdac;
+        bp.alpha = p.alpha; bp.ralpha = 1.0 / p.alpha; bp.lambdadalpha = p.lambda / p.alpha; bp.lambdac = L.lambdac;
         bp.dozim = p.dozim != 0; bp.nchan = nc; bp.tol = 0.0001 * 0.0001;       // :1353
         // rows to build: owned rows plus one halo row each side (pass 1 rebuilds p there)
         int ba = L.own0, bb = L.own1;
@@ -1043,7 +1043,7 @@ int octane_stage_build(octane_ctx* c, const float* d_u, const float* d_v, const 
     f.uh = (q.first_guess && lambdac_level != 0.f) ? B.uh : nullptr;
     f.vh = (q.first_guess && lambdac_level != 0.f) ? B.vh : nullptr;
     BuildParams bp;
-    bp.alpha = p->alpha; bp.lambdadalpha = p->lambda / p->alpha; bp.lambdac = lambdac_level;
+    bp.alpha = p->alpha; bp.ralpha = 1.0 / p->alpha; bp.lambdadalpha = p->lambda / p->alpha; bp.lambdac = lambdac_level;
     bp.dozim = p->dozim != 0; bp.nchan = nc; bp.tol = 0.0001 * 0.0001; bp.al1 = 1. - 0.5 * gnc;
     launch_build(f, B.pcg, g, 0, yi, 0, yi, bp, 0, st);
     // the 7 boundary-merged entries of the reference, expanded from the 5 stored planes

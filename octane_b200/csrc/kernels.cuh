@@ -45,6 +45,7 @@ enum { FINALIZE_BUILD = 0, FINALIZE_PASS1 = 1, FINALIZE_PASS2 = 2 };
 void launch_finalize(const PcgBuffers& b, int kind, float tol, cudaStream_t st);
 struct BuildParams {
     double alpha, lambdadalpha, al1;
+    double ralpha;             // RN(1/alpha), for the exact division shortcut of build.cu
     float lambdac;
     int dozim, nchan;
     float tol;

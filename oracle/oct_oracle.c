@@ -641,3 +641,45 @@ int oracle_pix2uv_ms(const oracle_nav *nav, double t1, double t2, const float *u
         }
     return 0;
 }
+
+/* ---- checks of the exact shortcuts taken by the CUDA build kernel (octane_b200/csrc/build.cu) ----
+ * The reference's promotion rules (:80,:102,:837-842) give float(1./double(s)) and double(x)/alpha
+ * with float s, x; the kernel computes the same values with a single-precision reciprocal and with
+ * multiply + one Markstein correction.  These enumerate / sample the operand space and count
+ * mismatches against the plain expressions. */
+long oracle_check_recip_float(unsigned stride, unsigned start)
+{
+    long bad = 0;
+    if (stride == 0) stride = 1;
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+    for (long long k = start; k < 0x100000000LL; k += stride) {
+        uint32_t b = (uint32_t)k;
+        float s;
+        memcpy(&s, &b, 4);
+        if (!(s == s) || s == 0.f || isinf(s)) continue;
+        volatile float via_double = (float)(1. / (double)s);   /* the reference's expression */
+        volatile float direct = 1.0f / s;                      /* IEEE single division == __frcp_rn */
+        if (via_double != direct) bad++;
+    }
+    return bad;
+}
+
+long oracle_check_div_const(double a, unsigned long long seed, long n)
+{
+    const double y = 1.0 / a;
+    long bad = 0;
+    unsigned long long s = seed ? seed : 88172645463325252ULL;
+    for (long k = 0; k < n; k++) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        uint32_t b = (uint32_t)(s >> 16);
+        float f;
+        memcpy(&f, &b, 4);
+        if (!(f == f) || isinf(f)) continue;
+        const double x = (double)f;
+        const double q = x * y;
+        const double r = fma(-q, a, x);
+        const double q1 = fma(r, y, q);
+        if (q1 != x / a) bad++;
+    }
+    return bad;
+}

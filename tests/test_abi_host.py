@@ -156,3 +156,18 @@ def test_gloo_world2_band_bootstrap_and_gather():
     assert all(r[3] == 2.0 for r in res)
     assert res[0][4][1] == res[1][4][0] == 256           # bands meet at the middle row
     assert res[0][4][3] > 256 and res[1][4][2] < 256     # and overlap in their inputs
+
+
+def test_exact_division_shortcuts(oracle):
+    """build.cu replaces the fp64 divisions the reference's promotion rules force with cheaper
+    sequences that must give the SAME float/double: float(1./double(s)) == 1.0f/s for every float s
+    (sampled with a stride over all bit patterns), and x*RN(1/a) + one Markstein step == double(x)/a."""
+    import ctypes as C
+    L = oracle.lib()
+    L.oracle_check_recip_float.argtypes = [C.c_uint, C.c_uint]
+    L.oracle_check_recip_float.restype = C.c_long
+    L.oracle_check_div_const.argtypes = [C.c_double, C.c_ulonglong, C.c_long]
+    L.oracle_check_div_const.restype = C.c_long
+    assert L.oracle_check_recip_float(61, 7) == 0
+    for a in (5.0, 3.0, 7.3, 0.1, 1e-3, 15.0, 1.0, 2.5, 123.456):
+        assert L.oracle_check_div_const(a, 12345, 2_000_000) == 0
