@@ -78,7 +78,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         self.proc.terminate()
         self.t.join(timeout=5)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             c = [x.strip() for x in ln.split(",")]
@@ -88,13 +88,17 @@ class ClockSampler:
                 sm.append(float(c[0])); mx.append(float(c[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(c[2]))
+            except ValueError:
+                pass
             for nm, val in zip(names, c[3:7]):
                 if val == "Active":
                     reasons.add(nm)
         # samples under load only (idle samples at the edges read the idle clock)
         load = [x for x in sm if x > 0.5 * max(sm)] if sm else []
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 def cpu_sample(nx, ny, sector, seed, size):
@@ -217,6 +221,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--max-disp", type=int, default=64)
+    ap.add_argument("--taper", type=int, default=None, help="developer: force the limb taper on (1) / off (0)")
+    ap.add_argument("--noise-floor", type=float, default=0.0, help="developer: add uniform noise of this amplitude to both frames")
+    ap.add_argument("--empty-cache", action="store_true", help="developer: release torch's cached blocks before the first solve")
     args = ap.parse_args()
     if args.size:
         sx, sy = (int(t) for t in args.size.split("x"))
@@ -245,6 +252,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     nx, ny, sector, taper = WORKLOADS[args.workload]
+    if args.taper is not None:
+        taper = bool(args.taper)
+        if taper:
+            sector = "fulldisk_0.5km"
     xs, ys, xo, yo, dt = S.SECTORS[sector]
     p = ob.default_params(max_disp=args.max_disp)
     ctx = ob.Context(local)
@@ -260,6 +271,14 @@ def main():
 
     # ---- synthetic inputs, resident in HBM (band rows [in0,in1) of the scene)
     img1, img2 = S.make_pair_torch(nx, ny, args.seed, dev, limb_taper=taper, rows=(in0, in1))
+    if args.noise_floor > 0:
+        g = torch.Generator(device=dev); g.manual_seed(1)
+        for im in (img1, img2):
+            for j0 in range(0, im.shape[0], 1024):
+                blk = im[j0:j0 + 1024]
+                blk.add_(torch.rand(blk.shape, device=dev, generator=g) * args.noise_floor)
+    if args.empty_cache:
+        torch.cuda.empty_cache()
     nown = own1 - own0
     u = torch.zeros((nown, nx), dtype=torch.float32, device=dev)
     v = torch.zeros_like(u)

@@ -22,6 +22,13 @@
  *                               src/oct_pix2uv_cuda.cu:279,291-297)
  *   octane_nav                 GOESNAVVar, include/goesread.h:3-14 (fields read by
  *                              src/oct_pix2uv_cuda.cu:27-172,295)
+ *   octane_navcal*             void oct_navcal_cuda(short*data2,short*data2s,short*x,short*y,short*xs,
+ *                              short*ys,int nx,int ny,int minx,int maxx,int miny,int maxy,float*data3,
+ *                              float*lat,float*lon,string cal,int datf,float xScale,...,int donav,OFFlags)
+ *                              src/oct_navcal_cuda.cu:100 (called by oct_goesread, src/oct_fileread.cc:383)
+ *   octane_uv2pix*             void oct_uv2pix(GOESVar&,float*u,float*v,double t2,OFFlags)
+ *                              src/oct_pix2uv_cuda.cu:372 (first-guess winds -> pixel displacements)
+ *   octane_band_minmax         void oct_bandminmax(int,float&,float&), src/oct_normalize_geo.cc:9
  * Image layout everywhere: row-major float32, index i + nx*j (+ nx*ny*c), i = x
  * (fastest), as the reference (src/oct_variational_optical_flow.cu:316-320).
  */
@@ -80,6 +87,21 @@ typedef struct octane_nav {
     float lat1, lon1, lon0, R;           /* polar / Mercator constants */
     int minX, minY;                      /* sector origin added to the pixel index, :192 */
 } octane_nav;
+
+/* Calibration / normalisation constants of one GOES-R L1b channel: the scalar arguments of
+ * oct_navcal_cuda (src/oct_navcal_cuda.cu:100-107) that are not already in octane_nav.
+ * The reference narrows req, rpol, pph+req and lam0 to float for this kernel; the library
+ * does the same from octane_nav. */
+typedef struct octane_cal {
+    float radScale, radOffset;           /* Rad:scale_factor, Rad:add_offset */
+    float fk1, fk2, bc1, bc2, kap1;      /* planck_fk1/fk2/bc1/bc2, kappa0 */
+    float maxin, minin;                  /* band radiance range (octane_band_minmax) */
+    float maxout, minout;                /* 255, 0 (src/oct_fileread.cc:341-342) */
+    float H;                             /* pph + req summed in float (src/oct_fileread.cc:306); 0: the
+                                            library forms it from octane_nav the same way */
+    int cal;                             /* 0 RAW (the only mode main.cc uses), 1 TEMP, 2 REF, 3 BRIT */
+    int donav;                           /* 1: fill lat/lon; 0: zeros */
+} octane_cal;
 
 /* Per-call statistics (filled by the last solve on the context). */
 #define OCTANE_MAX_SOLVES 256
@@ -141,6 +163,21 @@ int octane_optical_flow(octane_ctx* ctx, const float* img1, const float* img2, c
                         const octane_params* p, float* upix_inout, float* vpix_inout,
                         short* U, short* V, short* U_raw, short* V_raw, short* ctp, float* dT);
 
+/* Ingest: Rad counts -> 0..255 normalised brightness with the limb taper, and the latitude /
+ * longitude (degrees) of every pixel.  rad: ny*nx shorts; x: nx, y: ny fixed-grid counts;
+ * data/lat/lon: ny*nx floats out (lat and lon may both be NULL to skip navigation). */
+int octane_navcal(octane_ctx* ctx, const short* rad, const short* x, const short* y, int nx, int ny,
+                  const octane_nav* nav, const octane_cal* cal, float* data, float* lat, float* lon);
+/* ABI band table: radiance range used for the normalisation; returns 0, or -2 for an unknown band
+ * (the reference leaves maxch/minch uninitialised there). */
+int octane_band_minmax(int band, float* maxch, float* minch);
+/* First-guess winds (m/s, navigated) -> pixel displacements over t2-t1, in place.  lat/lon as
+ * octane_navcal produced them; x, y the fixed-grid counts.  All zeros when the sector moved
+ * (exact comparison of the offsets, src/oct_pix2uv_cuda.cu:421). */
+int octane_uv2pix(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
+                  const float* lat, const float* lon, const short* x, const short* y,
+                  int nx, int ny, const octane_params* p, float* u_inout, float* v_inout);
+
 /* ---- device-pointer entry points (stream-ordered on the ctx stream) ----- */
 /* All pointers are device memory on the context's device, dense (stride nx). */
 int octane_variational_flow_dev(octane_ctx* ctx, const float* d_img1, const float* d_img2,
@@ -149,6 +186,12 @@ int octane_variational_flow_dev(octane_ctx* ctx, const float* d_img1, const floa
 int octane_pix2uv_dev(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
                       const float* d_u, const float* d_v, int nx, int ny, const octane_params* p,
                       short* d_U, short* d_V, short* d_U_raw, short* d_V_raw);
+
+int octane_navcal_dev(octane_ctx* ctx, const short* d_rad, const short* d_x, const short* d_y, int nx, int ny,
+                      const octane_nav* nav, const octane_cal* cal, float* d_data, float* d_lat, float* d_lon);
+int octane_uv2pix_dev(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
+                      const float* d_lat, const float* d_lon, const short* d_x, const short* d_y,
+                      int nx, int ny, const octane_params* p, float* d_u_inout, float* d_v_inout);
 
 /* ---- stage entry points (device pointers; used by the parity tests) ----- */
 int octane_stage_blur_decimate(octane_ctx* ctx, const float* d_img, int nx, int ny, int nc,

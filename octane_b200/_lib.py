@@ -34,6 +34,14 @@ class Nav(C.Structure):
                 ("minX", C.c_int), ("minY", C.c_int)]
 
 
+class Cal(C.Structure):
+    """octane_cal: the scalar arguments of oct_navcal_cuda (reference src/oct_navcal_cuda.cu:100-107)."""
+    _fields_ = [("radScale", C.c_float), ("radOffset", C.c_float),
+                ("fk1", C.c_float), ("fk2", C.c_float), ("bc1", C.c_float), ("bc2", C.c_float), ("kap1", C.c_float),
+                ("maxin", C.c_float), ("minin", C.c_float), ("maxout", C.c_float), ("minout", C.c_float),
+                ("H", C.c_float), ("cal", C.c_int), ("donav", C.c_int)]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_levels", C.c_int), ("n_solves", C.c_int),
                 ("level_nx", C.c_int * 16), ("level_ny", C.c_int * 16),
@@ -53,6 +61,7 @@ EXPORTS = [
     "octane_get_stats", "octane_ctx_synchronize", "octane_ctx_stream", "octane_workspace_bytes", "octane_level_dims",
     "octane_variational_flow", "octane_pix2uv", "octane_optical_flow",
     "octane_variational_flow_dev", "octane_pix2uv_dev",
+    "octane_navcal", "octane_navcal_dev", "octane_band_minmax", "octane_uv2pix", "octane_uv2pix_dev",
     "octane_stage_blur_decimate", "octane_stage_gradient", "octane_stage_zoom_in",
     "octane_stage_build", "octane_stage_pcg",
     "octane_band_plan", "octane_comm_unique_id", "octane_comm_init", "octane_comm_rank",
@@ -95,6 +104,12 @@ def load() -> C.CDLL:
     L.octane_optical_flow.argtypes = [vp, vp, vp, vp, i, i, i, NP, d, d, PP, vp, vp, vp, vp, vp, vp, vp, fp]
     L.octane_variational_flow_dev.argtypes = [vp, vp, vp, i, i, i, PP, vp, vp]
     L.octane_pix2uv_dev.argtypes = [vp, NP, d, d, vp, vp, i, i, PP, vp, vp, vp, vp]
+    CP = C.POINTER(Cal)
+    L.octane_navcal.argtypes = [vp, vp, vp, vp, i, i, NP, CP, vp, vp, vp]
+    L.octane_navcal_dev.argtypes = [vp, vp, vp, vp, i, i, NP, CP, vp, vp, vp]
+    L.octane_band_minmax.argtypes = [i, fp, fp]
+    L.octane_uv2pix.argtypes = [vp, NP, d, d, vp, vp, vp, vp, i, i, PP, vp, vp]
+    L.octane_uv2pix_dev.argtypes = [vp, NP, d, d, vp, vp, vp, vp, i, i, PP, vp, vp]
     L.octane_stage_blur_decimate.argtypes = [vp, vp, i, i, i, f, vp]
     L.octane_stage_gradient.argtypes = [vp, vp, i, i, i, vp, vp]
     L.octane_stage_zoom_in.argtypes = [vp, vp, i, i, i, i, f, vp]

@@ -23,7 +23,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import Nav, Params, Stats
+from ._lib import Cal, Nav, Params, Stats
 
 ERRORS = {-1: "ENODEV", -2: "EINVAL", -3: "ENOMEM", -4: "ECUDA", -5: "EHALO", -6: "ECOMM"}
 
@@ -52,6 +52,25 @@ def goes_nav(xScale, yScale, xOffset, yOffset, pph=35786023.0, req=6378137.0, rp
     return Nav(pph, req, rpol, lam0, xScale, xOffset, yScale, yOffset,
                xOffset if g2xOffset is None else g2xOffset, yOffset if g2yOffset is None else g2yOffset,
                0.0, 0.0, 0.0, 6371000.0, minX, minY)
+
+
+def band_minmax(band: int):
+    """(maxch, minch) radiance range of ABI band 1..16 -- oct_bandminmax, src/oct_normalize_geo.cc:9."""
+    L = _lib.load()
+    a, b = C.c_float(), C.c_float()
+    rc = L.octane_band_minmax(band, C.byref(a), C.byref(b))
+    if rc < 0:
+        raise OctaneError(rc, L.octane_last_error().decode())
+    return a.value, b.value
+
+
+def goes_cal(radScale, radOffset, band=2, fk1=0.0, fk2=0.0, bc1=0.0, bc2=1.0, kap1=0.0, cal=0, donav=1,
+             maxin=None, minin=None) -> Cal:
+    """Calibration block as oct_goesread assembles it (src/oct_fileread.cc:341-388): band range from the
+    table, output range 0..255, cal "RAW"."""
+    mx, mn = band_minmax(band)
+    return Cal(radScale, radOffset, fk1, fk2, bc1, bc2, kap1, mx if maxin is None else maxin,
+               mn if minin is None else minin, 255.0, 0.0, 0.0, cal, donav)
 
 
 def level_dims(nx: int, ny: int, p: Optional[Params] = None):
@@ -247,6 +266,41 @@ class Context:
     def stage_zoom_in(self, d_flow, nx, ny, nxx, nyy, sf, d_out):
         self._after_torch()
         self._check(self._L.octane_stage_zoom_in(self._h, _ptr(d_flow), nx, ny, nxx, nyy, sf, _ptr(d_out)))
+
+    # ---- ingest (src/oct_navcal_cuda.cu:100) and first-guess conversion (src/oct_pix2uv_cuda.cu:372)
+    def oct_navcal_cuda(self, rad, x, y, nav: Nav, cal: Cal, data=None, lat=None, lon=None):
+        """rad: ny x nx int16 counts, x: nx, y: ny int16 fixed-grid counts.  numpy in -> numpy out
+        (host entry point); torch CUDA tensors -> device entry point.  Returns (data, lat, lon)."""
+        ny, nx = rad.shape
+        if _is_torch(rad):
+            import torch
+            mk = lambda: torch.empty((ny, nx), dtype=torch.float32, device=rad.device)   # noqa: E731
+            data = mk() if data is None else data
+            lat = mk() if lat is None else lat
+            lon = mk() if lon is None else lon
+            self._after_torch()
+            self._check(self._L.octane_navcal_dev(self._h, _ptr(rad), _ptr(x), _ptr(y), nx, ny, C.byref(nav),
+                                                  C.byref(cal), _ptr(data), _ptr(lat), _ptr(lon)))
+            return data, lat, lon
+        rad = np.ascontiguousarray(rad, np.int16); x = np.ascontiguousarray(x, np.int16); y = np.ascontiguousarray(y, np.int16)
+        data = np.empty((ny, nx), np.float32) if data is None else data
+        lat = np.empty((ny, nx), np.float32) if lat is None else lat
+        lon = np.empty((ny, nx), np.float32) if lon is None else lon
+        self._check(self._L.octane_navcal(self._h, _ptr(rad), _ptr(x), _ptr(y), nx, ny, C.byref(nav), C.byref(cal),
+                                          _ptr(data), _ptr(lat), _ptr(lon)))
+        return data, lat, lon
+
+    def oct_uv2pix(self, nav: Nav, t1: float, t2: float, lat, lon, x, y, u, v, p: Optional[Params] = None) -> int:
+        """u, v: first-guess winds (m/s) in, pixel displacements out (in place).  Returns 1 when the
+        sector-moved guard zeroed them."""
+        p = p or default_params()
+        ny, nx = u.shape
+        if _is_torch(u):
+            self._after_torch()
+            return self._check(self._L.octane_uv2pix_dev(self._h, C.byref(nav), t1, t2, _ptr(lat), _ptr(lon), _ptr(x),
+                                                         _ptr(y), nx, ny, C.byref(p), _ptr(u), _ptr(v)))
+        return self._check(self._L.octane_uv2pix(self._h, C.byref(nav), t1, t2, _ptr(lat), _ptr(lon), _ptr(x), _ptr(y),
+                                                 nx, ny, C.byref(p), _ptr(u), _ptr(v)))
 
     def stage_build(self, d_u, d_v, d_uh, d_vh, d_g1, d_g2, xi, yi, nc, p, lambdac, gnc, d_coef, d_bu, d_bv):
         self._after_torch()

@@ -645,9 +645,12 @@ void collect_stats(octane_ctx* c)
     const Level& F = pl.lv.back();
     s.finest_pixels = (long long)F.g.nx * (F.own1 - F.own0);
     double f1 = 0, f2 = 0; long long n1 = 0, n2 = 0;
+    // developer switch: one line per timed scope (category, level, solve, iteration, ms)
+    FILE* dump = (c->profile && getenv("OCTANE_DUMP_EVENTS")) ? fopen(getenv("OCTANE_DUMP_EVENTS"), "w") : nullptr;
     for (auto& e : c->events) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess) continue;
+        if (dump) fprintf(dump, "%d %d %d %d %.4f\n", e.cat, e.level, e.solve, e.ki, ms);
         switch (e.cat) {
             case CAT_PYR: s.ms_pyramid += ms; break;
             case CAT_BUILD: s.ms_build += ms; break;
@@ -665,6 +668,7 @@ void collect_stats(octane_ctx* c)
             } break;
         }
     }
+    if (dump) fclose(dump);
     s.finest_pass1_ms = n1 ? f1 / n1 : 0.0;
     s.finest_pass2_ms = n2 ? f2 / n2 : 0.0;
 }
@@ -906,6 +910,152 @@ int octane_optical_flow(octane_ctx* c, const float* img1, const float* img2, con
     CUDA_OK(cudaStreamSynchronize(c->stream));
     if (dT) *dT = (float)(t2 - t1);
     return nrc;
+}
+
+// ---- ingest: calibration / normalisation / lat-lon, first-guess conversion ------------------
+static void fill_cal(CalParams& c, const octane_nav* nav, const octane_cal* cal)
+{
+    c.xScale = nav->xScale; c.xOffset = nav->xOffset; c.yScale = nav->yScale; c.yOffset = nav->yOffset;
+    c.radScale = cal->radScale; c.radOffset = cal->radOffset;
+    // src/oct_fileread.cc:51,306: req, rpol, pph are read into floats, H = pph + req in float,
+    // lam0 = lam0*DTOR in float; oct_navcal_cuda takes them as float arguments
+    const float req = (float)nav->req, rpol = (float)nav->rpol, pph = (float)nav->pph;
+    c.req = req; c.rpol = rpol; c.H = (cal->H != 0.f) ? cal->H : pph + req; c.lam0 = (float)nav->lam0;
+    c.fk1 = cal->fk1; c.fk2 = cal->fk2; c.bc1 = cal->bc1; c.bc2 = cal->bc2; c.kap1 = cal->kap1;
+    c.maxin = cal->maxin; c.minin = cal->minin; c.maxout = cal->maxout; c.minout = cal->minout;
+    c.subpoint_slope = 1. / (0.021 - 0.0212);                       // src/oct_navcal_cuda.cu:178-179
+    c.subpoint_int = 1. - 0.021 * c.subpoint_slope;
+    c.cal = cal->cal; c.donav = cal->donav;
+}
+
+int octane_navcal_dev(octane_ctx* c, const short* d_rad, const short* d_x, const short* d_y, int nx, int ny,
+                      const octane_nav* nav, const octane_cal* cal, float* d_data, float* d_lat, float* d_lon)
+{
+    if (!c || !d_rad || !d_x || !d_y || !nav || !cal || !d_data || nx <= 0 || ny <= 0 || (!d_lat != !d_lon)) {
+        set_err("null or invalid argument");
+        return OCTANE_EINVAL;
+    }
+    CUDA_OK(cudaSetDevice(c->device));
+    CalParams cp;
+    fill_cal(cp, nav, cal);
+    launch_navcal(d_rad, d_x, d_y, nx, ny, cp, d_data, d_lat, d_lon, c->stream);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return OCTANE_OK;
+}
+
+int octane_navcal(octane_ctx* c, const short* rad, const short* x, const short* y, int nx, int ny,
+                  const octane_nav* nav, const octane_cal* cal, float* data, float* lat, float* lon)
+{
+    if (!c || !rad || !x || !y || !nav || !cal || !data || nx <= 0 || ny <= 0 || (!lat != !lon)) {
+        set_err("null or invalid argument");
+        return OCTANE_EINVAL;
+    }
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t n = (size_t)nx * ny, sb = n * sizeof(short), fb = n * sizeof(float);
+    const size_t xb = align_up((size_t)nx * sizeof(short)), yb = align_up((size_t)ny * sizeof(short));
+    int rc = ensure_stage(c, align_up(sb) + xb + yb + 3 * fb);
+    if (rc) return rc;
+    char* s = c->stage;
+    short* d_rad = (short*)s; s += align_up(sb);
+    short* d_x = (short*)s; s += xb;
+    short* d_y = (short*)s; s += yb;
+    float* d_data = (float*)s; s += fb;
+    float* d_lat = lat ? (float*)s : nullptr; s += fb;
+    float* d_lon = lon ? (float*)s : nullptr;
+    begin_call(c);
+    CUDA_OK(cudaMemcpyAsync(d_rad, rad, sb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_x, x, (size_t)nx * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_y, y, (size_t)ny * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+    rc = octane_navcal_dev(c, d_rad, d_x, d_y, nx, ny, nav, cal, d_data, d_lat, d_lon);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(data, d_data, fb, cudaMemcpyDeviceToHost, c->stream));
+    if (lat) {
+        CUDA_OK(cudaMemcpyAsync(lat, d_lat, fb, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(lon, d_lon, fb, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return OCTANE_OK;
+}
+
+// src/oct_normalize_geo.cc:9-88 (the table is data: ABI band radiance ranges; bands 7 and 8
+// carry the reference's "meteorological" ranges)
+int octane_band_minmax(int band, float* maxch, float* minch)
+{
+    static const float tab[16][2] = {
+        { 804.03605737f, -25.93664701f }, { 628.98723908f, -20.28991094f }, { 373.16695681f, -12.03764377f },
+        { 140.19342584f, -4.52236858f },  { 94.84802665f, -3.05961376f },   { 29.78947040f, -0.96095066f },
+        { 2.f, 0.f },                     { 6.f, 3.f },                     { 44.998f, -0.2472f },
+        { 79.831f, -0.2871f },            { 134.93f, -0.3909f },            { 108.44f, -0.4617f },
+        { 185.5699f, -1.6443f },          { 198.71f, -0.5154f },            { 212.28f, -0.5262f },
+        { 170.19f, -1.5726f } };
+    if (!maxch || !minch || band < 1 || band > 16) { set_err("unknown ABI band"); return OCTANE_EINVAL; }
+    *maxch = tab[band - 1][0];
+    *minch = tab[band - 1][1];
+    return OCTANE_OK;
+}
+
+int octane_uv2pix_dev(octane_ctx* c, const octane_nav* nav, double t1, double t2, const float* d_lat,
+                      const float* d_lon, const short* d_x, const short* d_y, int nx, int ny,
+                      const octane_params* p, float* d_u, float* d_v)
+{
+    if (!c || !nav || !d_lat || !d_lon || !d_x || !d_y || !p || !d_u || !d_v || nx <= 0 || ny <= 0) {
+        set_err("null or invalid argument");
+        return OCTANE_EINVAL;
+    }
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t fb = (size_t)nx * ny * sizeof(float);
+    // src/oct_pix2uv_cuda.cu:421: exact comparison; otherwise the first guess is zero (:464-474)
+    if (!((nav->xOffset == nav->g2xOffset) && (nav->yOffset == nav->g2yOffset))) {
+        CUDA_OK(cudaMemsetAsync(d_u, 0, fb, c->stream));
+        CUDA_OK(cudaMemsetAsync(d_v, 0, fb, c->stream));
+        return 1;
+    }
+    Uv2PixParams q;
+    q.secs = t2 - t1;
+    q.req = nav->req; q.rpol = nav->rpol; q.req2 = nav->req * nav->req; q.rpol2 = nav->rpol * nav->rpol;
+    double eval = sqrt((q.req2 - q.rpol2) / (q.req2));               // :417-428
+    q.eval = eval * eval;
+    q.lam0 = nav->lam0; q.pph = nav->pph;
+    q.xscale = nav->xScale; q.xoffset = nav->xOffset; q.yscale = nav->yScale; q.yoffset = nav->yOffset;
+    launch_uv2pix(d_u, d_v, d_lat, d_lon, d_x, d_y, nx, ny, q, c->stream);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return OCTANE_OK;
+}
+
+int octane_uv2pix(octane_ctx* c, const octane_nav* nav, double t1, double t2, const float* lat, const float* lon,
+                  const short* x, const short* y, int nx, int ny, const octane_params* p, float* u, float* v)
+{
+    if (!c || !nav || !lat || !lon || !x || !y || !p || !u || !v || nx <= 0 || ny <= 0) {
+        set_err("null or invalid argument");
+        return OCTANE_EINVAL;
+    }
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t n = (size_t)nx * ny, fb = n * sizeof(float);
+    const size_t xb = align_up((size_t)nx * sizeof(short)), yb = align_up((size_t)ny * sizeof(short));
+    int rc = ensure_stage(c, 4 * fb + xb + yb);
+    if (rc) return rc;
+    char* s = c->stage;
+    float* d_u = (float*)s; s += fb;
+    float* d_v = (float*)s; s += fb;
+    float* d_lat = (float*)s; s += fb;
+    float* d_lon = (float*)s; s += fb;
+    short* d_x = (short*)s; s += xb;
+    short* d_y = (short*)s;
+    begin_call(c);
+    CUDA_OK(cudaMemcpyAsync(d_u, u, fb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_v, v, fb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_lat, lat, fb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_lon, lon, fb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_x, x, (size_t)nx * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_y, y, (size_t)ny * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+    rc = octane_uv2pix_dev(c, nav, t1, t2, d_lat, d_lon, d_x, d_y, nx, ny, p, d_u, d_v);
+    if (rc < 0) return rc;
+    CUDA_OK(cudaMemcpyAsync(u, d_u, fb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(v, d_v, fb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return rc;
 }
 
 // ---- band planning / NCCL bootstrap ----------------------------------------------------------

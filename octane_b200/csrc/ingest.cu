@@ -1,0 +1,133 @@
+// ingest.cu -- the stages either side of the flow path that the reference also runs on the GPU:
+//   k_navcal : Rad counts -> radiance -> (optional calibration) -> limb taper -> 0..255
+//              normalisation, plus fixed-grid latitude / longitude of every pixel.
+//              Replaces octnavcalcuda, src/oct_navcal_cuda.cu:12-98 (reference tree).
+//   k_uv2pix : first-guess winds (m/s) -> pixel displacements by the haversine destination
+//              formula and the forward fixed-grid projection.
+//              Replaces octuv2xy + the host loops of oct_uv2pix, src/oct_pix2uv_cuda.cu:223-263,372-476.
+// Both are one pass over the scene (2 B in, 12 B out per pixel for navcal; 16 B in, 8 B out for
+// uv2pix); navcal with navigation is bound by its ~10 fp64 transcendentals per pixel, not by HBM.
+// The reference stages every operand through managed memory filled by single-threaded host
+// loops (including per-pixel index arrays icarr/jcarr/lxyzarr); here the pixel's (i, j) come
+// from the thread index and the coordinate vectors x[], y[] are read directly.
+// Expressions keep the reference's float/double promotion points.
+#include "kernels.cuh"
+
+namespace octane {
+
+__global__ void __launch_bounds__(256)
+k_navcal(const short* __restrict__ rad, const short* __restrict__ x, const short* __restrict__ y, int nx, int ny,
+         CalParams c, float* __restrict__ data3, float* __restrict__ lat, float* __restrict__ lon)
+{
+    const double PI = 3.14159265359;
+    const double DTOR = PI / 180.;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= nx || j >= ny) return;
+    const size_t lxyz = (size_t)j * nx + i;
+    const float xScale = c.xScale, xOffset = c.xOffset, yScale = c.yScale, yOffset = c.yOffset;
+    const float req = c.req, rpol = c.rpol, H = c.H, lam0 = c.lam0;
+    // :31-34 (float arithmetic, then widened)
+    double xVal = x[i] * xScale + xOffset;
+    double yVal = y[j] * yScale + yOffset;
+    double subpoint_dist = xVal * xVal + yVal * yVal;
+    float dVal = rad[lxyz] * c.radScale + c.radOffset;
+    if (lat && lon) {
+        if (c.donav == 1) {          // :36-49
+            double a, b, cc, rs, sx, sy, sz;
+            a = pow((sin(xVal)), 2) + pow(cos(xVal), 2) * (pow((cos(yVal)), 2) + (pow(req, 2)) / (pow(rpol, 2)) * pow((sin(yVal)), 2));
+            b = -2. * H * cos(xVal) * cos(yVal);
+            cc = pow(H, 2) - pow(req, 2);
+            rs = (-b - sqrt((pow(b, 2) - 4. * a * cc))) / (2. * a);
+            sx = rs * cos(xVal) * cos(yVal);
+            sy = -rs * sin(xVal);
+            sz = rs * cos(xVal) * sin(yVal);
+            float la = atan(double((pow(req, 2)) / (pow(rpol, 2))) * (sz / sqrt((pow((H - sx), 2) + pow(sy, 2)))));
+            float lo = lam0 - atan(sy / (H - sx));
+            la = la / DTOR;
+            lo = lo / DTOR;
+            lat[lxyz] = la;
+            lon[lxyz] = lo;
+        } else {
+            lat[lxyz] = 0.;
+            lon[lxyz] = 0.;
+        }
+    }
+    double dataF;
+    if (c.cal == 1) dataF = (c.fk2 / (log((c.fk1 / dVal) + 1.)) - c.bc1) / c.bc2;     // :59-63
+    else if (c.cal == 2) dataF = c.kap1 * dVal;                                         // :64-68
+    else dataF = dVal;                                                                  // RAW / BRIT / default
+    // limb taper, :80-91
+    float sdsconst;
+    if (subpoint_dist < 0.021) {
+        sdsconst = 1.;
+    } else {
+        if (subpoint_dist >= 0.0212) sdsconst = 0.;
+        else sdsconst = c.subpoint_slope * subpoint_dist + c.subpoint_int;
+    }
+    // :93
+    data3[lxyz] = sdsconst * (((dataF - c.minin) / (c.maxin - c.minin)) * (c.maxout - c.minout) + c.minout);
+}
+
+void launch_navcal(const short* rad, const short* x, const short* y, int nx, int ny, const CalParams& c,
+                   float* data, float* lat, float* lon, cudaStream_t st)
+{
+    dim3 grid((nx + 255) / 256, ny);
+    k_navcal<<<grid, 256, 0, st>>>(rad, x, y, nx, ny, c, data, lat, lon);
+}
+
+// One thread per pixel; u, v in: first-guess wind (m/s); out: displacement in pixels over `secs`.
+__global__ void __launch_bounds__(256)
+k_uv2pix(float* __restrict__ u, float* __restrict__ v, const float* __restrict__ lat, const float* __restrict__ lon,
+         const short* __restrict__ xs, const short* __restrict__ ys, int nx, int ny, Uv2PixParams q)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= nx || j >= ny) return;
+    const size_t lxyz = (size_t)j * nx + i;
+    const double R = 6371000.0;
+    const double pi = 3.14159265;
+    double rad = pi / 180.;
+    double H = q.pph + q.req;
+    // :236-244 (the host loop widened u, v, lat, lon to double, :408-413)
+    double u1 = u[lxyz];
+    double v1 = v[lxyz];
+    double latvalv = lat[lxyz];
+    double lonvalv = lon[lxyz];
+    double dist = sqrt(pow(u1, 2.0) + pow(v1, 2.0)) * (q.secs);
+    double brng = (180. + (90. - (atan2(-v1, -u1) / rad))) * rad;
+    double latorig = latvalv * rad;
+    latvalv = asin(sin(latorig) * cos(dist / R) + cos(latorig) * sin(dist / R) * cos(brng));
+    lonvalv = lonvalv * rad + (atan2((sin(brng) * sin(dist / R) * cos(latorig)), (cos(dist / R) - sin(latorig) * sin(latvalv))));
+    // :247-252
+    double thtc = atan(((q.rpol2) / (q.req2)) * tan(latvalv));
+    double rc = q.rpol / sqrt(1. - (q.eval) * pow(cos(thtc), 2.));
+    double sx = H - rc * cos(thtc) * cos(lonvalv - q.lam0);
+    double sy = -rc * cos(thtc) * sin(lonvalv - q.lam0);
+    double sz = rc * sin(thtc);
+    double x1v, y1v;
+    if ((H * (H - sx)) >= (sy * sy + ((q.req2) / (q.rpol2) * sz * sz))) {        // :253-261
+        x1v = (asin(-sy / (sqrt(sx * sx + sy * sy + sz * sz))) - q.xoffset) / q.xscale;
+        y1v = (atan(sz / sx) - q.yoffset) / q.yscale;
+    } else {
+        x1v = -999.;
+        y1v = -999.;
+    }
+    // :451-462
+    if (x1v > -998.) {
+        u[lxyz] = x1v - xs[i];
+        v[lxyz] = y1v - ys[j];
+    } else {
+        u[lxyz] = 0.;
+        v[lxyz] = 0.;
+    }
+}
+
+void launch_uv2pix(float* u, float* v, const float* lat, const float* lon, const short* xs, const short* ys, int nx,
+                   int ny, const Uv2PixParams& q, cudaStream_t st)
+{
+    dim3 grid((nx + 255) / 256, ny);
+    k_uv2pix<<<grid, 256, 0, st>>>(u, v, lat, lon, xs, ys, nx, ny, q);
+}
+
+}  // namespace octane

@@ -88,4 +88,23 @@ void launch_pix2uv(const NavParams& np, const float* u, const float* v, int nx, 
                    short* U, short* V, short* Uraw, short* Vraw, cudaStream_t st);
 void launch_ctp_pack(const float* cth, short* ctp, size_t n, int ir, cudaStream_t st);
 
+
+// ---- ingest.cu
+struct CalParams {
+    float xScale, xOffset, yScale, yOffset, radScale, radOffset;
+    float rpol, req, H, lam0;                 // narrowed to float as oct_navcal_cuda's arguments are
+    float fk1, fk2, bc1, bc2, kap1;
+    float maxin, minin, maxout, minout;
+    float subpoint_slope, subpoint_int;
+    int cal, donav;
+};
+void launch_navcal(const short* rad, const short* x, const short* y, int nx, int ny, const CalParams& c,
+                   float* data, float* lat, float* lon, cudaStream_t st);
+struct Uv2PixParams {
+    double secs, req, req2, rpol, rpol2, eval, lam0, pph;
+    float xscale, xoffset, yscale, yoffset;
+};
+void launch_uv2pix(float* u, float* v, const float* lat, const float* lon, const short* xs, const short* ys, int nx,
+                   int ny, const Uv2PixParams& q, cudaStream_t st);
+
 }  // namespace octane

@@ -7,8 +7,9 @@
 // rows ahead, completion signalled on mbarriers.  The v1 kernel kept one row of
 // loads in flight per warp and sat at 25 % occupancy waiting on the long
 // scoreboard (profiles/r01_ncu_pass1_v1_conus.txt: 57 % of DRAM peak); here the
-// bytes in flight are set by the ring depth (2 rows x 45 KB per SM), not by
-// registers.
+// bytes in flight are set by the ring depth (5 rows x 45 KB per SM), not by
+// registers: a consumer warp copies what it needs of a staged row into registers
+// and hands the stage straight back to the producer.
 //
 // One CTA per SM: 8 consumer warps (256 threads x 4 pixels = a 1024-pixel strip)
 // + 1 producer warp.  A task is a strip x row segment; tasks are dealt
@@ -19,6 +20,8 @@
 // W, A2, XU, XV are fetched for the task's own rows only, N also for the row above them.
 // Replaces jMatXVec/multiply_row + the p and x updates of
 // src/oct_variational_optical_flow.cu:112-139,1138-1146,1161,1172 (reference tree).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace octane {
@@ -27,12 +30,11 @@ namespace {
 
 constexpr int SWMAX = 1024;                 // pixels per strip (256 consumer threads x 4)
 constexpr int HALO = 4;                     // floats of left halo (keeps 16-byte alignment)
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 5;                   // 5 x 45.3 KB = 226 KB of the SM's 227 KB
 constexpr int HA = SWMAX + 2 * HALO;        // floats per halo array
 constexpr int NHALO = 7, NCENTRE = 4;
 constexpr int STAGE_FLOATS = NHALO * HA + NCENTRE * SWMAX;
 enum { XM_NONE = 0, XM_INIT = 1, XM_ACC = 2 };   // as in pcg.cu
-constexpr int CONSUMERS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
@@ -66,10 +68,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void stg4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float& el(float4& v, int k) { return reinterpret_cast<float*>(&v)[k]; }
-__device__ __forceinline__ const float& el(const float4& v, int k) { return reinterpret_cast<const float*>(&v)[k]; }
+// PX consecutive pixels per thread (2 or 4), moved as one float2 / float4
+template <int PX> struct Px { float v[PX]; };
+template <int PX> __device__ __forceinline__ Px<PX> ldv(const float* p);
+template <> __device__ __forceinline__ Px<4> ldv<4>(const float* p)
+{
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    Px<4> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+template <> __device__ __forceinline__ Px<2> ldv<2>(const float* p)
+{
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    Px<2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
+}
+__device__ __forceinline__ void stv(float* p, const Px<4>& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+__device__ __forceinline__ void stv(float* p, const Px<2>& a) { *reinterpret_cast<float2*>(p) = make_float2(a.v[0], a.v[1]); }
+template <int PX> __device__ __forceinline__ Px<PX> zerov()
+{
+    Px<PX> r;
+#pragma unroll
+    for (int k = 0; k < PX; k++) r.v[k] = 0.f;
+    return r;
+}
 
 struct TArgs {
     PcgBuffers b;
@@ -82,68 +102,68 @@ struct TArgs {
     int nstrips, nsegs;
 };
 
-struct PRowT {
-    float4 pu, pv, a1, a4;
-    float eu_l, ev_l, eu_r, ev_r;     // p of the pixels just left / right of the WARP's 128 pixels
+template <int PX> struct PRowT {
+    Px<PX> pu, pv, a1, a4;
+    float eu_l, ev_l, eu_r, ev_r;     // p of the pixels just left / right of the WARP's 32*PX pixels
 };
 
 __device__ __forceinline__ float mul_lo(int i, int n) { return i == 0 ? 0.f : (i == n - 1 ? 2.f : 1.f); }
 __device__ __forceinline__ float mul_hi(int i, int n) { return i == n - 1 ? 0.f : (i == 0 ? 2.f : 1.f); }
 
-// p_new of one staged row for this thread's 4 pixels (+ the warp-edge pixels in lanes 0 / 31);
+// p_new of one staged row for this thread's PX pixels (+ the warp-edge pixels in lanes 0 / 31);
 // when `xdst` is set (the row is one of the task's own), also the previous iteration's pending
 // x += alpha_prev p_old (:1172), written straight to global memory.
-template <int XM>
-__device__ __forceinline__ PRowT p_from_stage(const float* st, int i0s, int tcol, int nx, int lane, float beta,
-                                              float alpha_prev, float* xu_dst, float* xv_dst)
+template <int XM, int PX>
+__device__ __forceinline__ PRowT<PX> p_from_stage(const float* st, int i0s, int tcol, int nx, int lane, float beta,
+                                                  float alpha_prev, float* xu_dst, float* xv_dst)
 {
     constexpr bool FIRST = (XM == XM_NONE);
-    // tcol = 4*tid: this thread's first pixel inside the strip; halo arrays are shifted by HALO
+    // tcol = PX*tid: this thread's first pixel inside the strip; halo arrays are shifted by HALO
     const float* RU = st;
     const float* RV = st + HA;
     const float* PU = st + 2 * HA;
     const float* PV = st + 3 * HA;
     const float* A1 = st + 4 * HA;
     const float* A4 = st + 5 * HA;
-    PRowT o;
-    o.pu = o.pv = make_float4(0.f, 0.f, 0.f, 0.f);
+    PRowT<PX> o;
+    o.pu = o.pv = zerov<PX>();
     o.eu_l = o.ev_l = o.eu_r = o.ev_r = 0.f;
     const int c = tcol + HALO;
-    const float4 ru = lds4(RU + c), rv = lds4(RV + c);
-    o.a1 = lds4(A1 + c);
-    o.a4 = lds4(A4 + c);
-    float4 po_u = make_float4(0.f, 0.f, 0.f, 0.f), po_v = po_u;
-    if (!FIRST) { po_u = lds4(PU + c); po_v = lds4(PV + c); }
+    const Px<PX> ru = ldv<PX>(RU + c), rv = ldv<PX>(RV + c);
+    o.a1 = ldv<PX>(A1 + c);
+    o.a4 = ldv<PX>(A4 + c);
+    Px<PX> po_u = zerov<PX>(), po_v = po_u;
+    if (!FIRST) { po_u = ldv<PX>(PU + c); po_v = ldv<PX>(PV + c); }
     if (!FIRST && xu_dst) {
-        float4 x_u = make_float4(0.f, 0.f, 0.f, 0.f), x_v = x_u;
+        Px<PX> x_u = zerov<PX>(), x_v = x_u;
         if (XM == XM_ACC) {
             const float* XU = st + NHALO * HA + 2 * SWMAX;
-            x_u = lds4(XU + tcol);
-            x_v = lds4(XU + SWMAX + tcol);
+            x_u = ldv<PX>(XU + tcol);
+            x_v = ldv<PX>(XU + SWMAX + tcol);
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < PX; k++) {
             if (i0s + tcol + k < nx) {
-                el(x_u, k) = fmaf(alpha_prev, el(po_u, k), el(x_u, k));
-                el(x_v, k) = fmaf(alpha_prev, el(po_v, k), el(x_v, k));
+                x_u.v[k] = fmaf(alpha_prev, po_u.v[k], x_u.v[k]);
+                x_v.v[k] = fmaf(alpha_prev, po_v.v[k], x_v.v[k]);
             } else {
-                el(x_u, k) = 0.f; el(x_v, k) = 0.f;
+                x_u.v[k] = 0.f; x_v.v[k] = 0.f;
             }
         }
-        stg4(xu_dst, x_u);
-        stg4(xv_dst, x_v);
+        stv(xu_dst, x_u);
+        stv(xv_dst, x_v);
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < PX; k++) {
         if (i0s + tcol + k < nx) {
-            const float mu = 1.0f / el(o.a1, k), mv = 1.0f / el(o.a4, k);      // jDiagInv, :142-149
-            const float zu = mu * el(ru, k), zv = mv * el(rv, k);              // z = Minv r, :1138
-            el(o.pu, k) = FIRST ? zu : fmaf(beta, el(po_u, k), zu);            // p = Bk p + z, :1146
-            el(o.pv, k) = FIRST ? zv : fmaf(beta, el(po_v, k), zv);
+            const float mu = 1.0f / o.a1.v[k], mv = 1.0f / o.a4.v[k];          // jDiagInv, :142-149
+            const float zu = mu * ru.v[k], zv = mv * rv.v[k];                  // z = Minv r, :1138
+            o.pu.v[k] = FIRST ? zu : fmaf(beta, po_u.v[k], zu);                // p = Bk p + z, :1146
+            o.pv.v[k] = FIRST ? zv : fmaf(beta, po_v.v[k], zv);
         }
     }
     if (lane == 0 || lane == 31) {
-        const int ce = (lane == 0) ? c - 1 : c + 4;          // column just outside the warp's 128 pixels
+        const int ce = (lane == 0) ? c - 1 : c + PX;         // column just outside the warp's 32*PX pixels
         const int ie = i0s + ce - HALO;
         if (ie >= 0 && ie < nx) {
             const float mu = 1.0f / A1[ce], mv = 1.0f / A4[ce];
@@ -156,10 +176,14 @@ __device__ __forceinline__ PRowT p_from_stage(const float* st, int i0s, int tcol
     return o;
 }
 
-template <int XM>
-__global__ void __launch_bounds__(CONSUMERS + 32, 1) k_pcg_pass1_tma(TArgs a)
+// The stencil row is latency-bound per warp (dependent FMA chains, shared-memory loads, shuffles),
+// so what keeps the copy engine busy is the number of consumer warps: PX = 2 runs 16 of them
+// (512 threads x 2 pixels), PX = 4 runs 8.
+template <int XM, int PX>
+__global__ void __launch_bounds__(SWMAX / PX + 32, 1) k_pcg_pass1_tma(TArgs a)
 {
     constexpr bool FIRST = (XM == XM_NONE);
+    constexpr int CONSUMERS = SWMAX / PX;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red[32];
     __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE];
@@ -223,7 +247,7 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 1) k_pcg_pass1_tma(TArgs a)
         const float beta = FIRST ? 0.f : s->rz / s->rz_old;           // Bk, :1144
         const float alpha_prev = FIRST ? 0.f : s->alpha;
         const int lane = tid & 31;
-        const int tcol = tid * 4;
+        const int tcol = tid * PX;
         float* pu_new = a.b.pu[a.cur ^ 1];
         float* pv_new = a.b.pv[a.cur ^ 1];
         uint32_t it = 0;
@@ -233,108 +257,110 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 1) k_pcg_pass1_tma(TArgs a)
             const int i0 = i0s + tcol;
             const int j_a = a.ja + seg * a.rs, j_b = min(a.jb, j_a + a.rs);
             const bool active = tcol < a.sw && i0 < g.nx;
-            PRowT up, ce, dn;
-            up.pu = up.pv = up.a1 = up.a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            PRowT<PX> up, ce, dn;
+            const Px<PX> zero = zerov<PX>();
+            up.pu = up.pv = up.a1 = up.a4 = zero;
             up.eu_l = up.ev_l = up.eu_r = up.ev_r = 0.f;
             ce = up;
-            float4 n_up = make_float4(0.f, 0.f, 0.f, 0.f);       // N of the row above the centre row
-            float4 n_ce = n_up;                                  // N of the row that is about to become the centre
-            int prev_stage = -1;                       // stage holding the centre row's coefficients
+            Px<PX> n_up = zero;                        // N of the row above the centre row
+            Px<PX> n_ce = zero;                        // N, a2, W (+ W of column i0-1) of the centre row
+            Px<PX> a2_ce = zero, w_ce = zero;
+            float wl_ce = 0.f;
             for (int jr = j_a - 1; jr <= j_b; jr++) {
-                int stg = -1;
-                float4 n_dn = make_float4(0.f, 0.f, 0.f, 0.f);
+                Px<PX> n_dn = zero, a2_dn = zero, w_dn = zero;
+                float wl_dn = 0.f;
                 if (jr >= 0 && jr < g.ny) {
-                    stg = it % NSTAGE;
+                    const int stg = it % NSTAGE;
                     mbar_wait(&full_bar[stg], (it / NSTAGE) & 1u);
                     it++;
                     const float* st = stages + (size_t)stg * STAGE_FLOATS;
-                    const bool own = active && jr >= j_a && jr < j_b;
+                    const bool centre = jr >= j_a && jr < j_b;
+                    const bool own = active && centre;
                     const size_t xoff = own ? g.at(i0, jr) : 0;
-                    dn = p_from_stage<XM>(st, i0s, tcol, g.nx, lane, beta, alpha_prev,
-                                          own ? a.b.xu + xoff : nullptr, own ? a.b.xv + xoff : nullptr);
-                    if (!active) { dn.pu = dn.pv = make_float4(0.f, 0.f, 0.f, 0.f); }
-                    if (active && jr < j_b) n_dn = lds4(st + NHALO * HA + SWMAX + tcol);
+                    dn = p_from_stage<XM, PX>(st, i0s, tcol, g.nx, lane, beta, alpha_prev,
+                                              own ? a.b.xu + xoff : nullptr, own ? a.b.xv + xoff : nullptr);
+                    if (!active) { dn.pu = dn.pv = zero; }
+                    if (active && jr < j_b) n_dn = ldv<PX>(st + NHALO * HA + SWMAX + tcol);
+                    if (own) {
+                        // everything the row needs as a centre row goes to registers now, so the stage
+                        // returns to the producer at once (bytes in flight = the whole ring)
+                        a2_dn = ldv<PX>(st + NHALO * HA + tcol);
+                        const float* Wrow = st + 6 * HA + HALO + tcol;
+                        w_dn = ldv<PX>(Wrow);
+                        wl_dn = (i0 > 0) ? Wrow[-1] : 0.f;     // column i0-1 (never staged at the image edge)
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[stg]);
                 } else {
-                    dn.pu = dn.pv = dn.a1 = dn.a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    dn.pu = dn.pv = dn.a1 = dn.a4 = zero;
                     dn.eu_l = dn.ev_l = dn.eu_r = dn.ev_r = 0.f;
                 }
                 const int jc = jr - 1;                 // centre row: up = jc-1, ce = jc, dn = jc+1
                 if (jc >= j_a && jc < j_b) {
-                    float lu = __shfl_up_sync(0xffffffffu, ce.pu.w, 1), lv = __shfl_up_sync(0xffffffffu, ce.pv.w, 1);
-                    float ru_ = __shfl_down_sync(0xffffffffu, ce.pu.x, 1), rv_ = __shfl_down_sync(0xffffffffu, ce.pv.x, 1);
+                    float lu = __shfl_up_sync(0xffffffffu, ce.pu.v[PX - 1], 1), lv = __shfl_up_sync(0xffffffffu, ce.pv.v[PX - 1], 1);
+                    float ru_ = __shfl_down_sync(0xffffffffu, ce.pu.v[0], 1), rv_ = __shfl_down_sync(0xffffffffu, ce.pv.v[0], 1);
                     if (lane == 0) { lu = ce.eu_l; lv = ce.ev_l; }
                     if (lane == 31) { ru_ = ce.eu_r; rv_ = ce.ev_r; }
                     if (active) {
-                        const float* pst = stages + (size_t)prev_stage * STAGE_FLOATS;
-                        const float4 a2 = lds4(pst + NHALO * HA + tcol);
-                        const float* Wrow = pst + 6 * HA + HALO + tcol;
-                        const float4 w = lds4(Wrow);
-                        const float wl = (i0 > 0) ? Wrow[-1] : 0.f;     // column i0-1 (never staged at the image edge)
                         const float m6 = mul_lo(jc, g.ny), m8 = mul_hi(jc, g.ny);
-                        float4 qu, qv;
+                        Px<PX> qu, qv;
                         float part = 0.f;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const float pl_u = (k == 0) ? lu : el(ce.pu, k - 1), pl_v = (k == 0) ? lv : el(ce.pv, k - 1);
-                            const float pr_u = (k == 3) ? ru_ : el(ce.pu, k + 1), pr_v = (k == 3) ? rv_ : el(ce.pv, k + 1);
-                            const float a5 = mul_lo(i0 + k, g.nx) * ((k == 0) ? wl : el(w, k - 1));
-                            const float a7 = mul_hi(i0 + k, g.nx) * el(w, k);
-                            const float a6 = m6 * el(n_up, k), a8 = m8 * el(n_ce, k);
+                        for (int k = 0; k < PX; k++) {
+                            const float pl_u = (k == 0) ? lu : ce.pu.v[k > 0 ? k - 1 : 0], pl_v = (k == 0) ? lv : ce.pv.v[k > 0 ? k - 1 : 0];
+                            const float pr_u = (k == PX - 1) ? ru_ : ce.pu.v[k < PX - 1 ? k + 1 : 0];
+                            const float pr_v = (k == PX - 1) ? rv_ : ce.pv.v[k < PX - 1 ? k + 1 : 0];
+                            const float a5 = mul_lo(i0 + k, g.nx) * ((k == 0) ? wl_ce : w_ce.v[k > 0 ? k - 1 : 0]);
+                            const float a7 = mul_hi(i0 + k, g.nx) * w_ce.v[k];
+                            const float a6 = m6 * n_up.v[k], a8 = m8 * n_ce.v[k];
                             float su = 0.f;                       // multiply_row order: [j-1] [i-1] a1 a2 [i+1] [j+1]
-                            su = fmaf(a6, el(up.pu, k), su);
+                            su = fmaf(a6, up.pu.v[k], su);
                             su = fmaf(a5, pl_u, su);
-                            su = fmaf(el(ce.a1, k), el(ce.pu, k), su);
-                            su = fmaf(el(a2, k), el(ce.pv, k), su);
+                            su = fmaf(ce.a1.v[k], ce.pu.v[k], su);
+                            su = fmaf(a2_ce.v[k], ce.pv.v[k], su);
                             su = fmaf(a7, pr_u, su);
-                            su = fmaf(a8, el(dn.pu, k), su);
+                            su = fmaf(a8, dn.pu.v[k], su);
                             float sv = 0.f;
-                            sv = fmaf(a6, el(up.pv, k), sv);
+                            sv = fmaf(a6, up.pv.v[k], sv);
                             sv = fmaf(a5, pl_v, sv);
-                            sv = fmaf(el(a2, k), el(ce.pu, k), sv);
-                            sv = fmaf(el(ce.a4, k), el(ce.pv, k), sv);
+                            sv = fmaf(a2_ce.v[k], ce.pu.v[k], sv);
+                            sv = fmaf(ce.a4.v[k], ce.pv.v[k], sv);
                             sv = fmaf(a7, pr_v, sv);
-                            sv = fmaf(a8, el(dn.pv, k), sv);
+                            sv = fmaf(a8, dn.pv.v[k], sv);
                             const bool in = i0 + k < g.nx;
-                            el(qu, k) = in ? su : 0.f;
-                            el(qv, k) = in ? sv : 0.f;
-                            if (in) part += el(ce.pu, k) * su + el(ce.pv, k) * sv;
+                            qu.v[k] = in ? su : 0.f;
+                            qv.v[k] = in ? sv : 0.f;
+                            if (in) part += ce.pu.v[k] * su + ce.pv.v[k] * sv;
                         }
                         const size_t off = g.at(i0, jc);
-                        stg4(pu_new + off, ce.pu);
-                        stg4(pv_new + off, ce.pv);
-                        stg4(a.b.qu + off, qu);
-                        stg4(a.b.qv + off, qv);
+                        stv(pu_new + off, ce.pu);
+                        stv(pv_new + off, ce.pv);
+                        stv(a.b.qu + off, qu);
+                        stv(a.b.qv + off, qv);
                         dot[0] += (double)part;
                     }
                 } else if (a.store_halo && active && jc >= 0 && jc < g.ny &&
                            ((jc == a.ja - 1 && j_a == a.ja) || (jc == a.jb && j_b == a.jb))) {
                     // banded runs keep p on the halo rows for the next iteration's p_old
-                    stg4(pu_new + g.at(i0, jc), ce.pu);
-                    stg4(pv_new + g.at(i0, jc), ce.pv);
+                    stv(pu_new + g.at(i0, jc), ce.pu);
+                    stv(pv_new + g.at(i0, jc), ce.pv);
                 }
-                // the centre row's stage is no longer needed: hand it back to the producer
-                if (prev_stage >= 0) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[prev_stage]);
-                }
-                prev_stage = stg;
                 up = ce;
                 ce = dn;
                 n_up = n_ce;
                 n_ce = n_dn;
+                a2_ce = a2_dn;
+                w_ce = w_dn;
+                wl_ce = wl_dn;
             }
             // last staged row of the task (row j_b, or none when j_b == ny)
             if (a.store_halo && active && j_b == a.jb && j_b < g.ny) {
-                stg4(pu_new + g.at(i0, j_b), ce.pu);
-                stg4(pv_new + g.at(i0, j_b), ce.pv);
-            }
-            if (prev_stage >= 0) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[prev_stage]);
+                stv(pu_new + g.at(i0, j_b), ce.pu);
+                stv(pv_new + g.at(i0, j_b), ce.pv);
             }
         }
     }
-    // ---------------- p.q: fixed-order block + grid reduction (all 288 threads) ----------------
+    // ---------------- p.q: fixed-order block + grid reduction (all threads) -------------------
     block_sum<1>(dot, red);
     double tot[1];
     if (grid_sum_finish<1>(dot, a.b.partials, a.b.ticket, tot, red)) {
@@ -357,9 +383,13 @@ void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, in
 {
     TArgs a;
     a.b = b; a.g = g; a.ja = ja; a.jb = jb; a.cur = ki & 1; a.store_halo = store_halo;
+    // developer switches for layout experiments: forced strip width / rows per task
+    static const int force_sw = getenv("OCTANE_P1_SW") ? atoi(getenv("OCTANE_P1_SW")) : 0;
+    static const int force_rs = getenv("OCTANE_P1_RS") ? atoi(getenv("OCTANE_P1_RS")) : 0;
     a.nstrips = (g.nx + SWMAX - 1) / SWMAX;
     a.sw = round_up((g.nx + a.nstrips - 1) / a.nstrips, 32);
     if (a.sw > SWMAX) a.sw = SWMAX;
+    if (force_sw >= 32 && force_sw <= SWMAX) a.sw = round_up(force_sw, 32);
     a.nstrips = (g.nx + a.sw - 1) / a.sw;
     // rows per task: minimise rounds x (rows + 2 halo rows) over the persistent grid
     const int nrows = jb - ja;
@@ -372,22 +402,36 @@ void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, in
         const double cost = (double)rounds * (rs + 2 + 3);      // +3: pipeline fill per task
         if (cost < best_cost) { best_cost = cost; best_rs = rs; }
     }
-    a.rs = best_rs;
+    a.rs = force_rs > 0 ? force_rs : best_rs;
     a.nsegs = (nrows + a.rs - 1) / a.rs;
     const int ntasks = a.nstrips * a.nsegs;
     int grid = ntasks < sm_count ? ntasks : sm_count;
     if (grid > b.max_partial_blocks) grid = b.max_partial_blocks;
     const size_t smem = (size_t)NSTAGE * STAGE_FLOATS * sizeof(float);
+    // developer switch: pixels per consumer thread (2 -> 16 consumer warps, 4 -> 8)
+    static const int px = (getenv("OCTANE_P1_PX") && atoi(getenv("OCTANE_P1_PX")) == 4) ? 4 : 2;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    if (ki == 0)      k_pcg_pass1_tma<XM_NONE><<<grid, CONSUMERS + 32, smem, st>>>(a);
-    else if (ki == 1) k_pcg_pass1_tma<XM_INIT><<<grid, CONSUMERS + 32, smem, st>>>(a);
-    else              k_pcg_pass1_tma<XM_ACC><<<grid, CONSUMERS + 32, smem, st>>>(a);
+    const int xm = ki == 0 ? XM_NONE : (ki == 1 ? XM_INIT : XM_ACC);
+    if (px == 2) {
+        const int threads = SWMAX / 2 + 32;
+        if (xm == XM_NONE)      k_pcg_pass1_tma<XM_NONE, 2><<<grid, threads, smem, st>>>(a);
+        else if (xm == XM_INIT) k_pcg_pass1_tma<XM_INIT, 2><<<grid, threads, smem, st>>>(a);
+        else                    k_pcg_pass1_tma<XM_ACC, 2><<<grid, threads, smem, st>>>(a);
+    } else {
+        const int threads = SWMAX / 4 + 32;
+        if (xm == XM_NONE)      k_pcg_pass1_tma<XM_NONE, 4><<<grid, threads, smem, st>>>(a);
+        else if (xm == XM_INIT) k_pcg_pass1_tma<XM_INIT, 4><<<grid, threads, smem, st>>>(a);
+        else                    k_pcg_pass1_tma<XM_ACC, 4><<<grid, threads, smem, st>>>(a);
+    }
 }
 
 }  // namespace octane

@@ -9,6 +9,12 @@
 //   void oct_pix2uv_cuda(GOESVar&, double, float*, float*, short*, short*, short*, short*, OFFlags)
 //        replaces src/oct_pix2uv_cuda.cu:265
 //
+//   void oct_navcal_cuda(short*, short*, short*, short*, short*, short*, int, int, int, int, int, int,
+//                        float*, float*, float*, std::string, int, float x19, int, OFFlags)
+//        replaces src/oct_navcal_cuda.cu:100 (ingest: calibration, normalisation, lat/lon)
+//   void oct_uv2pix(GOESVar&, float*, float*, double, OFFlags)
+//        replaces src/oct_pix2uv_cuda.cu:372 (first-guess winds -> pixel displacements)
+//
 // on top of the C ABI in include/octane_b200.h, so that a maintainer drops the
 // two .cu objects from the reference's link line, adds this file and
 // -loctane_b200, and every caller above (oct_optical_flow.cc:67,91, main.cc:439)
@@ -22,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <string>
 
 #include "image.h"      // before goesread.h, which uses Image without including it
 #include "goesread.h"
@@ -107,4 +114,53 @@ void oct_pix2uv_cuda(GOESVar& goesData, double t2, float* uarr, float* varr, sho
         std::cout << "MOVE WARNING: Sector Moved, setting motions to 0 " << g.xOffset << " " << g.g2xOffset << " "
                   << g.yOffset << " " << g.g2yOffset << std::endl;
     goesData.dT = dT;          // src/oct_pix2uv_cuda.cu:347,357,369
+}
+
+namespace {
+void nav_from(const GOESNAVVar& g, octane_nav* nav)
+{
+    nav->pph = g.pph; nav->req = g.req; nav->rpol = g.rpol; nav->lam0 = g.lam0;
+    nav->xScale = g.xScale; nav->xOffset = g.xOffset; nav->yScale = g.yScale; nav->yOffset = g.yOffset;
+    nav->g2xOffset = g.g2xOffset; nav->g2yOffset = g.g2yOffset;
+    nav->lat1 = g.lat1; nav->lon1 = g.lon1; nav->lon0 = g.lon0; nav->R = g.R;
+    nav->minX = g.minX; nav->minY = g.minY;
+}
+}  // namespace
+
+// Ingest stage called by the GOES reader (src/oct_fileread.cc:359-388).  Like the reference
+// wrapper it also fills the sector copies data2s / xs / ys (src/oct_navcal_cuda.cu:145-176).
+void oct_navcal_cuda(short* data2, short* data2s, short* x, short* y, short* xs, short* ys, int nx, int ny, int minx,
+                     int maxx, int miny, int maxy, float* data3, float* lat, float* lon, std::string cal, int /*datf*/,
+                     float xScale, float xOffset, float yScale, float yOffset, float radScale, float radOffset,
+                     float rpol, float req, float H, float lam0, float fk1, float fk2, float bc1, float bc2, float kap1,
+                     float maxin, float minin, float maxout, float minout, int donav, OFFlags args)
+{
+    octane_ctx* c = context_for(args.setdevice);
+    const int sx = maxx - minx, sy = maxy - miny;
+    for (int l = miny; l < maxy && l < ny; l++) {
+        for (int i = minx; i < maxx && i < nx; i++) data2s[(long)(i - minx) + (long)sx * (l - miny)] = data2[(long)i + (long)nx * l];
+        ys[l - miny] = y[l];
+    }
+    for (int i = minx; i < maxx && i < nx; i++) xs[i - minx] = x[i];
+    octane_nav nav = {};
+    nav.req = req; nav.rpol = rpol; nav.pph = 0.; nav.lam0 = lam0;
+    nav.xScale = xScale; nav.xOffset = xOffset; nav.yScale = yScale; nav.yOffset = yOffset;
+    octane_cal k = {};
+    k.radScale = radScale; k.radOffset = radOffset; k.fk1 = fk1; k.fk2 = fk2; k.bc1 = bc1; k.bc2 = bc2; k.kap1 = kap1;
+    k.maxin = maxin; k.minin = minin; k.maxout = maxout; k.minout = minout; k.H = H;
+    k.cal = (cal == "TEMP") ? 1 : (cal == "REF") ? 2 : (cal == "BRIT") ? 3 : 0;      // :115-118
+    k.donav = donav;
+    if (octane_navcal(c, data2s, xs, ys, sx, sy, &nav, &k, data3, lat, lon) < 0) die("oct_navcal_cuda");
+}
+
+void oct_uv2pix(GOESVar& goesData, float* u, float* v, double t2, OFFlags args)
+{
+    octane_params p;
+    params_from(args, &p);
+    octane_ctx* c = context_for(args.setdevice);
+    octane_nav nav;
+    nav_from(goesData.nav, &nav);
+    if (octane_uv2pix(c, &nav, goesData.t, t2, goesData.latVal, goesData.lonVal, goesData.x, goesData.y,
+                      (int)goesData.nav.nx, (int)goesData.nav.ny, &p, u, v) < 0)
+        die("oct_uv2pix");
 }

@@ -683,3 +683,109 @@ long oracle_check_div_const(double a, unsigned long long seed, long n)
     }
     return bad;
 }
+
+/* ---- ingest: octnavcalcuda, src/oct_navcal_cuda.cu:12-98 (host wrapper :100-207) ---------------
+ * Calibration constants as oct_navcal_cuda receives them (all float).  cal: 0 RAW, 1 TEMP, 2 REF,
+ * 3 BRIT.  lat/lon may be NULL. */
+typedef struct {
+    float xScale, xOffset, yScale, yOffset, radScale, radOffset;
+    float rpol, req, H, lam0;
+    float fk1, fk2, bc1, bc2, kap1;
+    float maxin, minin, maxout, minout;
+    int cal, donav;
+} oracle_cal;
+
+int oracle_navcal(const short *rad, const short *x, const short *y, int nx, int ny, const oracle_cal *c,
+                  float *data3, float *lat, float *lon)
+{
+    const double PI = 3.14159265359, DTOR = PI / 180.;
+    const float subpoint_slope = 1. / (0.021 - 0.0212);            /* :178-179 */
+    const float subpoint_int = 1. - 0.021 * subpoint_slope;
+    const float req = c->req, rpol = c->rpol, H = c->H;
+    const float req2 = req * req, rpol2 = rpol * rpol;             /* pow(float,int) is float on the device */
+    const float ratio = req2 / rpol2;
+    const float cterm = H * H - req2;
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) {
+            const size_t k = (size_t)j * nx + i;
+            /* :31-34: short*float+float in float (an FMA on the GPU), then widened */
+            double xVal = fmaf((float)x[i], c->xScale, c->xOffset);
+            double yVal = fmaf((float)y[j], c->yScale, c->yOffset);
+            double subpoint_dist = xVal * xVal + yVal * yVal;
+            float dVal = fmaf((float)rad[k], c->radScale, c->radOffset);
+            if (lat && lon) {
+                if (c->donav == 1) {                               /* :36-49 */
+                    double sxv = sin(xVal), cxv = cos(xVal), syv = sin(yVal), cyv = cos(yVal);
+                    double a = sxv * sxv + cxv * cxv * (cyv * cyv + (double)ratio * (syv * syv));
+                    double b = -2. * H * cxv * cyv;
+                    double cc = cterm;
+                    double rs = (-b - sqrt((b * b - 4. * a * cc))) / (2. * a);
+                    double sx = rs * cxv * cyv;
+                    double sy = -rs * sxv;
+                    double sz = rs * cxv * syv;
+                    float la = atan((double)ratio * (sz / sqrt(((H - sx) * (H - sx) + sy * sy))));
+                    float lo = c->lam0 - atan(sy / (H - sx));
+                    la = la / DTOR;
+                    lo = lo / DTOR;
+                    lat[k] = la; lon[k] = lo;
+                } else {
+                    lat[k] = 0.f; lon[k] = 0.f;
+                }
+            }
+            double dataF;
+            if (c->cal == 1) dataF = (c->fk2 / (log((c->fk1 / dVal) + 1.)) - c->bc1) / c->bc2;
+            else if (c->cal == 2) dataF = c->kap1 * dVal;
+            else dataF = dVal;
+            float sdsconst;                                        /* :80-91 */
+            if (subpoint_dist < 0.021) sdsconst = 1.f;
+            else if (subpoint_dist >= 0.0212) sdsconst = 0.f;
+            else sdsconst = subpoint_slope * subpoint_dist + subpoint_int;
+            data3[k] = sdsconst * (((dataF - c->minin) / (c->maxin - c->minin)) * (c->maxout - c->minout) + c->minout);
+        }
+    return 0;
+}
+
+/* ---- first guess: octuv2xy + oct_uv2pix, src/oct_pix2uv_cuda.cu:223-263,372-476 ----------------
+ * u, v in: wind (m/s); out: pixel displacement.  Returns 1 when the sector-moved guard zeroed it. */
+int oracle_uv2pix(const oracle_nav *nav, double t1, double t2,
+                  const float *lat, const float *lon, const short *xs, const short *ys, int nx, int ny,
+                  float *u, float *v)
+{
+    const size_t n = (size_t)nx * ny;
+    if (!((nav->xOffset == nav->g2xOffset) && (nav->yOffset == nav->g2yOffset))) {     /* :421, :464-474 */
+        for (size_t k = 0; k < n; k++) { u[k] = 0.f; v[k] = 0.f; }
+        return 1;
+    }
+    const double R = 6371000.0, pi = 3.14159265, rad = pi / 180.;
+    const double req = nav->req, rpol = nav->rpol, req2 = req * req, rpol2 = rpol * rpol;
+    double eval = sqrt((req2 - rpol2) / (req2));
+    eval = eval * eval;
+    const double H = nav->pph + req, secs = t2 - t1, lam0 = nav->lam0;
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) {
+            const size_t k = (size_t)j * nx + i;
+            double u1 = u[k], v1 = v[k], latvalv = lat[k], lonvalv = lon[k];
+            double dist = sqrt(u1 * u1 + v1 * v1) * (secs);
+            double brng = (180. + (90. - (atan2(-v1, -u1) / rad))) * rad;
+            double latorig = latvalv * rad;
+            latvalv = asin(sin(latorig) * cos(dist / R) + cos(latorig) * sin(dist / R) * cos(brng));
+            lonvalv = lonvalv * rad + (atan2((sin(brng) * sin(dist / R) * cos(latorig)), (cos(dist / R) - sin(latorig) * sin(latvalv))));
+            double thtc = atan(((rpol2) / (req2)) * tan(latvalv));
+            double rc = rpol / sqrt(1. - (eval) * (cos(thtc) * cos(thtc)));
+            double sx = H - rc * cos(thtc) * cos(lonvalv - lam0);
+            double sy = -rc * cos(thtc) * sin(lonvalv - lam0);
+            double sz = rc * sin(thtc);
+            double x1v, y1v;
+            if ((H * (H - sx)) >= (sy * sy + ((req2) / (rpol2) * sz * sz))) {
+                x1v = (asin(-sy / (sqrt(sx * sx + sy * sy + sz * sz))) - nav->xOffset) / nav->xScale;
+                y1v = (atan(sz / sx) - nav->yOffset) / nav->yScale;
+            } else {
+                x1v = -999.; y1v = -999.;
+            }
+            if (x1v > -998.) { u[k] = x1v - xs[i]; v[k] = y1v - ys[j]; }
+            else { u[k] = 0.f; v[k] = 0.f; }
+        }
+    return 0;
+}

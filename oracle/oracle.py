@@ -46,6 +46,27 @@ class RefParams(C.Structure):
 RefNav = OracleNav  # same field order in oracle/ref_driver.cc
 
 
+class OracleCal(C.Structure):
+    """the float scalars oct_navcal_cuda receives (src/oct_navcal_cuda.cu:100-107)"""
+    _fields_ = [("xScale", C.c_float), ("xOffset", C.c_float), ("yScale", C.c_float), ("yOffset", C.c_float),
+                ("radScale", C.c_float), ("radOffset", C.c_float),
+                ("rpol", C.c_float), ("req", C.c_float), ("H", C.c_float), ("lam0", C.c_float),
+                ("fk1", C.c_float), ("fk2", C.c_float), ("bc1", C.c_float), ("bc2", C.c_float), ("kap1", C.c_float),
+                ("maxin", C.c_float), ("minin", C.c_float), ("maxout", C.c_float), ("minout", C.c_float),
+                ("cal", C.c_int), ("donav", C.c_int)]
+
+
+RefCal = OracleCal  # same field order in oracle/ref_driver.cc
+
+
+def goes_cal(nav, radScale, radOffset, maxin, minin, fk1=0.0, fk2=0.0, bc1=0.0, bc2=1.0, kap1=0.0, cal=0, donav=1):
+    """as oct_goesread assembles the call (src/oct_fileread.cc:51,306,341-388): req, rpol, pph, lam0 are floats there"""
+    f = np.float32
+    return OracleCal(nav.xScale, nav.xOffset, nav.yScale, nav.yOffset, radScale, radOffset,
+                     f(nav.rpol), f(nav.req), f(f(nav.pph) + f(nav.req)), f(nav.lam0),
+                     fk1, fk2, bc1, bc2, kap1, maxin, minin, 255.0, 0.0, cal, donav)
+
+
 def params(alpha=5.0, lambda_=1.0, lambdac=0.0, scaleF=0.5, kiters=4, liters=3, cgiters=30, dozim=1):
     return OracleParams(alpha, lambda_, lambdac, scaleF, kiters, liters, cgiters, dozim)
 
@@ -141,6 +162,28 @@ def pix2uv_ms(nav, t1, t2, u, v, flags=0):
     return a, b
 
 
+def navcal(rad, x, y, cal):
+    rad = np.ascontiguousarray(rad, np.int16); x = np.ascontiguousarray(x, np.int16); y = np.ascontiguousarray(y, np.int16)
+    ny, nx = rad.shape
+    L = lib()
+    L.oracle_navcal.argtypes = [_i16, _i16, _i16, C.c_int, C.c_int, C.POINTER(OracleCal), _f32, _f32, _f32]
+    data = np.zeros((ny, nx), np.float32); lat = np.zeros((ny, nx), np.float32); lon = np.zeros((ny, nx), np.float32)
+    L.oracle_navcal(rad, x, y, nx, ny, C.byref(cal), data, lat, lon)
+    return data, lat, lon
+
+
+def uv2pix(nav, t1, t2, lat, lon, x, y, u, v):
+    """returns (u_pix, v_pix, rc); inputs are not modified"""
+    L = lib()
+    L.oracle_uv2pix.argtypes = [C.POINTER(OracleNav), C.c_double, C.c_double, _f32, _f32, _i16, _i16, C.c_int, C.c_int,
+                                _f32, _f32]
+    u = np.array(u, np.float32, copy=True); v = np.array(v, np.float32, copy=True)
+    ny, nx = u.shape
+    rc = L.oracle_uv2pix(C.byref(nav), t1, t2, np.ascontiguousarray(lat, np.float32), np.ascontiguousarray(lon, np.float32),
+                         np.ascontiguousarray(x, np.int16), np.ascontiguousarray(y, np.int16), nx, ny, u, v)
+    return u, v, rc
+
+
 # ---- the reference itself -------------------------------------------------
 _ref_cpu = None
 _ref_cuda = None
@@ -168,6 +211,7 @@ def ref_cuda():
                                        C.c_double, C.c_double, C.POINTER(RefParams),
                                        _f32, _f32, _i16, _i16, _i16, _i16, C.c_void_p, C.POINTER(C.c_float)]
         L.ref_patch_match.argtypes = [_f32, _f32, _f32, _f32, C.c_int, C.c_int, C.POINTER(RefParams)]
+        ingest_argtypes(L)
         _ref_cuda = L
     return _ref_cuda
 
@@ -182,6 +226,7 @@ def ref_shim():
     if _ref_shim is None:
         L = C.CDLL(os.path.join(HERE, "_ref", "libref_shim.so"))
         L.ref_optical_flow.argtypes = ref_cuda_argtypes()
+        ingest_argtypes(L)
         _ref_shim = L
     return _ref_shim
 
@@ -189,6 +234,34 @@ def ref_shim():
 def ref_cuda_argtypes():
     return [_f32, _f32, C.c_void_p, C.c_int, C.c_int, C.POINTER(RefNav), C.c_double, C.c_double,
             C.POINTER(RefParams), _f32, _f32, _i16, _i16, _i16, _i16, C.c_void_p, C.POINTER(C.c_float)]
+
+
+def ingest_argtypes(L):
+    L.ref_navcal.argtypes = [_i16, _i16, _i16, C.c_int, C.c_int, C.POINTER(RefCal), C.POINTER(RefParams), _f32, _f32, _f32]
+    L.ref_uv2pix.argtypes = [C.POINTER(RefNav), C.c_double, C.c_double, _f32, _f32, _i16, _i16, C.c_int, C.c_int,
+                             C.POINTER(RefParams), _f32, _f32]
+
+
+def ref_navcal(rad, x, y, cal, L=None):
+    """oct_navcal_cuda() of library L (ref_cuda(): the reference; ref_shim(): our shim under the reference's signature)"""
+    L = L or ref_cuda()
+    rad = np.ascontiguousarray(rad, np.int16); x = np.ascontiguousarray(x, np.int16); y = np.ascontiguousarray(y, np.int16)
+    ny, nx = rad.shape
+    data = np.zeros((ny, nx), np.float32); lat = np.zeros((ny, nx), np.float32); lon = np.zeros((ny, nx), np.float32)
+    rp = ref_params()
+    bad = L.ref_navcal(rad, x, y, nx, ny, C.byref(cal), C.byref(rp), data, lat, lon)
+    assert bad == 0, "sector copies data2s/xs/ys differ from the inputs"
+    return data, lat, lon
+
+
+def ref_uv2pix(nav, t1, t2, lat, lon, x, y, u, v, L=None):
+    L = L or ref_cuda()
+    u = np.array(u, np.float32, copy=True); v = np.array(v, np.float32, copy=True)
+    ny, nx = u.shape
+    rp = ref_params(dofirstguess=1)
+    L.ref_uv2pix(C.byref(nav), t1, t2, np.ascontiguousarray(lat, np.float32), np.ascontiguousarray(lon, np.float32),
+                 np.ascontiguousarray(x, np.int16), np.ascontiguousarray(y, np.int16), nx, ny, C.byref(rp), u, v)
+    return u, v
 
 
 def ref_dispatch(L, img1, img2, nav, t1, t2, rp=None, cth=None):

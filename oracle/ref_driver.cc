@@ -12,6 +12,8 @@
 //   oct_optical_flow               src/oct_optical_flow.cc:21
 //   oct_patch_match_optical_flow   src/oct_patch_match_optical_flow.cc:56
 //   oct_zoom_out / oct_zoom_in     src/oct_zoom.cc:17,154
+//   oct_navcal_cuda                src/oct_navcal_cuda.cu:100
+//   oct_uv2pix                     src/oct_pix2uv_cuda.cu:372
 // Only tests/, __graft_entry__.smoke() and bench.py's baseline legs load it.
 #include <cstring>
 #include <string>
@@ -26,6 +28,10 @@ void oct_zoom_in(double*, double*, int, int, int, int);
 void oct_variational_optical_flow(Image, Image, float*, float*, float*, int, int, int, OFFlags);
 void oct_pix2uv_cuda(GOESVar&, double, float*, float*, short*, short*, short*, short*, OFFlags);
 int oct_optical_flow(GOESVar&, GOESVar&, OFFlags&);
+void oct_uv2pix(GOESVar&, float*, float*, double, OFFlags);
+void oct_navcal_cuda(short*, short*, short*, short*, short*, short*, int, int, int, int, int, int, float*, float*,
+                     float*, std::string, int, float, float, float, float, float, float, float, float, float, float,
+                     float, float, float, float, float, float, float, float, float, int, OFFlags);
 #endif
 
 // Flat parameter block shared with Python (ctypes); order matters.
@@ -143,6 +149,46 @@ int ref_optical_flow(const float* g1, const float* g2, const float* cth, int nx,
     std::memcpy(vr2, d1.vVal2, n * sizeof(short));
     if (a.doCTH == 1 && ctp) std::memcpy(ctp, d1.CTP, n * sizeof(short));
     *dT = d1.dT;
+    return 0;
+}
+
+// Ingest stage as the GOES reader calls it (src/oct_fileread.cc:383-388): full sector, cal "RAW".
+struct RefCal {
+    float xScale, xOffset, yScale, yOffset, radScale, radOffset;
+    float rpol, req, H, lam0;
+    float fk1, fk2, bc1, bc2, kap1;
+    float maxin, minin, maxout, minout;
+    int cal, donav;
+};
+int ref_navcal(const short* rad, const short* x, const short* y, int nx, int ny, const RefCal* c,
+               const RefParams* p, float* data3, float* lat, float* lon)
+{
+    OFFlags a; defaults(a, p);
+    const size_t n = (size_t)nx * ny;
+    short* data2s = new short[n];
+    short* xs = new short[nx];
+    short* ys = new short[ny];
+    const char* names[4] = { "RAW", "TEMP", "REF", "BRIT" };
+    oct_navcal_cuda(const_cast<short*>(rad), data2s, const_cast<short*>(x), const_cast<short*>(y), xs, ys, nx, ny, 0, nx,
+                    0, ny, data3, lat, lon, names[c->cal & 3], 0, c->xScale, c->xOffset, c->yScale, c->yOffset,
+                    c->radScale, c->radOffset, c->rpol, c->req, c->H, c->lam0, c->fk1, c->fk2, c->bc1, c->bc2, c->kap1,
+                    c->maxin, c->minin, c->maxout, c->minout, c->donav, a);
+    int bad = std::memcmp(data2s, rad, n * sizeof(short)) != 0 || std::memcmp(xs, x, nx * sizeof(short)) != 0 ||
+              std::memcmp(ys, y, ny * sizeof(short)) != 0;
+    delete[] data2s; delete[] xs; delete[] ys;
+    return bad;
+}
+
+int ref_uv2pix(const RefNav* nav, double t1, double t2, const float* lat, const float* lon, const short* x,
+               const short* y, int nx, int ny, const RefParams* p, float* u, float* v)
+{
+    OFFlags a; defaults(a, p);
+    GOESVar g;
+    fill_nav(g.nav, nav, nx, ny);
+    g.t = t1;
+    g.latVal = const_cast<float*>(lat); g.lonVal = const_cast<float*>(lon);
+    g.x = const_cast<short*>(x); g.y = const_cast<short*>(y);
+    oct_uv2pix(g, u, v, t2, a);
     return 0;
 }
 #endif

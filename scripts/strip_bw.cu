@@ -4,6 +4,7 @@
 //   layout 0: row-major planes (the product's layout): elem (i,j) of plane k at k*P + j*pitch + i
 //   layout 1: strip-major planes: k*P + (strip*ny + j)*SW + (i - strip*SW)
 //   layout 2: planes interleaved by row: (j*NARR + k)*pitch + i
+//   layout 3: row-major planes, every second plane of a twice larger arena (address span x2)
 // build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o strip_bw strip_bw.cu
 // run:   ./strip_bw nx ny layout [nin nout rs]
 #include <cuda_runtime.h>
@@ -47,6 +48,7 @@ struct Args {
 __device__ __forceinline__ size_t addr(const Args& a, int k, int strip, int j)
 {
     if (a.layout == 0) return (size_t)k * a.P + (size_t)j * a.pitch + (size_t)strip * SW;
+    if (a.layout == 3) return (size_t)(2 * k) * a.P + (size_t)j * a.pitch + (size_t)strip * SW;
     if (a.layout == 1) return (size_t)k * a.P + ((size_t)strip * a.ny + j) * SW;
     return ((size_t)j * a.narr + k) * a.pitch + (size_t)strip * SW;
 }
@@ -129,7 +131,7 @@ int main(int argc, char** argv)
         }
     }
     a.rs = rs; a.nsegs = (a.ny + rs - 1) / rs;
-    const size_t bytes = a.P * a.narr * sizeof(float);
+    const size_t bytes = a.P * a.narr * sizeof(float) * (a.layout == 3 ? 2 : 1);
     if (cudaMalloc(&a.base, bytes) != cudaSuccess) { printf("alloc of %.1f GB failed\n", bytes / 1e9); return 1; }
     cudaMemset(a.base, 0, bytes);
     const size_t smem = (size_t)NSTAGE * MAXIN * SW * sizeof(float);

@@ -82,3 +82,67 @@ def nav_constants(c):
         dt = 3600.0
     flags = dict(pixuv=c.get("pixuv", 0), dopolar=int(kind == "polar"), domerc=int(kind == "merc"))
     return kw, extra, 1000.0, 1000.0 + dt, flags
+
+
+# ---- ingest (oct_navcal_cuda) and first-guess conversion (oct_uv2pix) ---------------------------
+INGEST = {
+    # band-2 mesoscale sector, far from the limb
+    "ingest_meso_b2": dict(sector="meso_0.5km", nx=160, ny=120, x0=0, y0=0, band=2, maxin=628.98723908, minin=-20.28991094,
+                           radScale=0.1586, radOffset=-20.29),
+    # full-disk window straddling the limb taper x^2+y^2 in [0.021, 0.0212) and the off-earth corner
+    "ingest_limb_b13": dict(sector="fulldisk_0.5km", nx=480, ny=440, x0=3150, y0=3150, band=13, maxin=185.5699, minin=-1.6443,
+                            radScale=0.04572, radOffset=-1.6443),
+    # no navigation requested (second file of a pair: donav = 0)
+    "ingest_nonav": dict(sector="meso_2km", nx=96, ny=64, x0=40, y0=10, band=2, maxin=628.98723908, minin=-20.28991094,
+                         radScale=0.1586, radOffset=-20.29, donav=0),
+}
+
+UV2PIX = {
+    "uv2pix_meso": dict(ingest="ingest_meso_b2"),
+    "uv2pix_limb": dict(ingest="ingest_limb_b13"),
+    "uv2pix_moved": dict(ingest="ingest_meso_b2", moved=True),
+}
+
+
+def ingest_inputs(c):
+    """(rad counts, x counts, y counts, nav kwargs) of an ingest case; counts are seeded 12-bit radiances"""
+    nx, ny = c["nx"], c["ny"]
+    rng = np.random.default_rng(sum(map(ord, c["sector"])) + nx)
+    y, x = np.mgrid[0:ny, 0:nx].astype(np.float32)
+    rad = (2000 + 1500 * np.sin(x / 9.0) * np.cos(y / 7.0) + rng.integers(-200, 200, (ny, nx))).astype(np.int16)
+    rad[0, 0] = 0; rad[1, 1] = 4095; rad[2, 2] = -1          # extremes / fill-like value
+    xs, ys, xo, yo, dt = S.SECTORS[c["sector"]]
+    xc = (np.arange(nx) + c["x0"]).astype(np.int16)
+    yc = (np.arange(ny) + c["y0"]).astype(np.int16)
+    return rad, xc, yc, dict(xScale=xs, yScale=ys, xOffset=xo, yOffset=yo), dt
+
+
+def uv2pix_winds(nx, ny):
+    y, x = np.mgrid[0:ny, 0:nx].astype(np.float32)
+    u = (12.0 * np.sin(x / 31.0) + 6.0 * np.cos(y / 23.0) + 3.0).astype(np.float32)
+    v = (-9.0 * np.cos(x / 27.0) * np.sin(y / 19.0) - 2.0).astype(np.float32)
+    u[0, 0] = 0.0; v[0, 0] = 0.0
+    return u, v
+
+
+def ingest_r2(c):
+    """x^2 + y^2 (rad^2) of every pixel of an ingest case: the limb cut of oct_navcal_cuda.cu:80-91 is at 0.0212"""
+    _, xc, yc, kw, _ = ingest_inputs(c)
+    xv = xc.astype(np.float64) * kw["xScale"] + kw["xOffset"]
+    yv = yc.astype(np.float64) * kw["yScale"] + kw["yOffset"]
+    return xv[None, :] ** 2 + yv[:, None] ** 2
+
+
+def check_latlon(lat, lon, wlat, wlon, r2):
+    """lat/lon parity: 2 float ulps (3e-5 deg at |lon| < 256) where the image is used (inside the limb cut);
+    between the cut and the earth's edge the fixed-grid inverse is ill-conditioned (sqrt of a vanishing
+    discriminant, src/oct_navcal_cuda.cu:41) and last-bit differences of sin/cos grow: 2e-3 deg there.
+    Off-earth pixels (NaN) must coincide."""
+    assert np.array_equal(np.isnan(lat), np.isnan(wlat)) and np.array_equal(np.isnan(lon), np.isnan(wlon))
+    ok = ~np.isnan(lat)
+    inner = ok & (r2 < 0.0212)
+    outer = ok & ~inner
+    for a, b in ((lat, wlat), (lon, wlon)):
+        d = np.abs(a - b)
+        assert d[inner].max(initial=0) <= 3.1e-5, d[inner].max(initial=0)
+        assert d[outer].max(initial=0) <= 2e-3, d[outer].max(initial=0)

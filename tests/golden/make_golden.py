@@ -20,8 +20,34 @@ import cases  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 
+def ingest(out):
+    """fixtures of the ingest stage (oct_navcal_cuda) and the first-guess conversion (oct_uv2pix)"""
+    made = {}
+    for name, c in cases.INGEST.items():
+        rad, xc, yc, kw, dt = cases.ingest_inputs(c)
+        nav = O.goes_nav(**kw)
+        cal = O.goes_cal(nav, c["radScale"], c["radOffset"], c["maxin"], c["minin"], donav=c.get("donav", 1))
+        data, lat, lon = O.ref_navcal(rad, xc, yc, cal)
+        made[name] = (lat, lon, xc, yc, kw, dt)
+        np.savez_compressed(os.path.join(out, name + ".npz"), rad=rad, x=xc, y=yc, data=data, lat=lat, lon=lon)
+        print(name, "data range", float(data.min()), float(data.max()), "zeros", int((data == 0).sum()),
+              "lat range", float(np.nanmin(lat)), float(np.nanmax(lat)), "nan", int(np.isnan(lat).sum()), flush=True)
+    for name, c in cases.UV2PIX.items():
+        lat, lon, xc, yc, kw, dt = made[c["ingest"]]
+        kw = dict(kw)
+        if c.get("moved"):
+            kw.update(g2xOffset=kw["xOffset"] + 0.001, g2yOffset=kw["yOffset"])
+        nav = O.goes_nav(**kw)
+        u, v = cases.uv2pix_winds(len(xc), len(yc))
+        up, vp = O.ref_uv2pix(nav, 1000.0, 1000.0 + dt, lat, lon, xc, yc, u, v)
+        np.savez_compressed(os.path.join(out, name + ".npz"), u=u, v=v, upix=up, vpix=vp)
+        print(name, "upix range", float(np.nanmin(up)), float(np.nanmax(up)), "zeros", int((up == 0).sum()), flush=True)
+
+
 def main(out):
     os.makedirs(out, exist_ok=True)
+    if "--ingest-only" in sys.argv:
+        return ingest(out)
     for name, c in cases.VARIATIONAL.items():
         img1, img2, u0, v0 = cases.variational_inputs(c)
         kw = dict(c.get("params", {}))
@@ -66,7 +92,8 @@ def main(out):
                             uPix=up, vPix=vp, U=outs[0], V=outs[1], U_raw=outs[2], V_raw=outs[3], CTP=outs[4],
                             dT=np.float32(dT.value))
         print("dispatch ir", ir, "CTP range", int(outs[4].min()), int(outs[4].max()), flush=True)
+    ingest(out)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
+    main(sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else os.path.join(ROOT, "gpurun_out", "golden"))

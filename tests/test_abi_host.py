@@ -40,14 +40,14 @@ def test_struct_layout_matches_header():
     code = r'''
 #include <stdio.h>
 #include "octane_b200.h"
-int main(){printf("%zu %zu %zu\n", sizeof(octane_params), sizeof(octane_nav), sizeof(octane_stats));return 0;}
+int main(){printf("%zu %zu %zu %zu\n", sizeof(octane_params), sizeof(octane_nav), sizeof(octane_stats), sizeof(octane_cal));return 0;}
 '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(code)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
-        a, b, c = map(int, subprocess.check_output([os.path.join(d, "t")]).split())
-    assert (a, b, c) == (C.sizeof(ob.Params), C.sizeof(ob.Nav), C.sizeof(ob.Stats))
+        a, b, c, e = map(int, subprocess.check_output([os.path.join(d, "t")]).split())
+    assert (a, b, c, e) == (C.sizeof(ob.Params), C.sizeof(ob.Nav), C.sizeof(ob.Stats), C.sizeof(ob.Cal))
 
 
 def test_defaults_are_the_reference_defaults():
@@ -171,3 +171,12 @@ def test_exact_division_shortcuts(oracle):
     assert L.oracle_check_recip_float(61, 7) == 0
     for a in (5.0, 3.0, 7.3, 0.1, 1e-3, 15.0, 1.0, 2.5, 123.456):
         assert L.oracle_check_div_const(a, 12345, 2_000_000) == 0
+
+
+def test_band_table_matches_reference_values():
+    """octane_band_minmax == oct_bandminmax (reference src/oct_normalize_geo.cc:9-88); needs no GPU."""
+    assert ob.band_minmax(2) == pytest.approx((628.98723908, -20.28991094), rel=1e-7)
+    assert ob.band_minmax(13) == pytest.approx((185.5699, -1.6443), rel=1e-7)
+    assert ob.band_minmax(7) == (2.0, 0.0) and ob.band_minmax(8) == (6.0, 3.0)    # the "meteorological" ranges
+    with pytest.raises(ob.OctaneError):
+        ob.band_minmax(17)
