@@ -43,6 +43,7 @@ struct Flags {                 // OFFlags, include/offlags.h:4-72 (fields this p
          setNormMin3 = true;
     std::string ftype = "GOES";
     int dump_settings = 0;     // -dump_settings: print the parsed flags as key=value lines and exit (tests)
+    int dry_run = 0;           // -dry_run: read the inputs and write outfile.nc with zero motion, no GPU work (tests of the I/O)
 };
 
 struct Scene {                 // the parts of GOESVar / GOESNAVVar the GOES path fills
@@ -324,6 +325,7 @@ int main(int argc, char* argv[])
         if (s == "-normmin3") { args.NormMin3 = (float)atof(nxt); args.setNormMin3 = false; }
         if (s == "-o") outdir = nxt;
         if (s == "-dump_settings") args.dump_settings = 1;
+        if (s == "-dry_run") args.dry_run = 1;
     }
     // :362-392
     args.oftype = (args.dozim == 0) ? 3 : 1;
@@ -355,6 +357,25 @@ int main(int argc, char* argv[])
     const int nx = g1.nx, ny = g1.ny;
     const size_t n = (size_t)nx * ny;
 
+    if (args.dry_run) {
+        octane_nav nav0;
+        memset(&nav0, 0, sizeof nav0);
+        nav0.pph = g1.pph; nav0.req = g1.req; nav0.rpol = g1.rpol; nav0.lam0 = g1.lam0;
+        nav0.xScale = g1.xScale; nav0.xOffset = g1.xOffset; nav0.yScale = g1.yScale; nav0.yOffset = g1.yOffset;
+        nav0.g2xOffset = g2.xOffset; nav0.g2yOffset = g2.yOffset;
+        if (octane_band_minmax(g1.band, &args.NormMax, &args.NormMin)) return fail("band_id outside 1..16");
+        std::vector<short> z(n, 0);
+        std::vector<float> zf(n, 0.f), cth0;
+        if (args.doCTH == 1 && !read_plane(f1c, "Cloud_Top_Height_Effective", nx, ny, cth0, &err)) return fail(err);
+        for (size_t k = 0; k < cth0.size(); k++) z[k] = args.ir == 1 ? (short)((cth0[k] - 300) * 100) : (short)cth0[k];
+        std::vector<short> zero(n, 0);
+        const std::string outname0 = outdir + "outfile.nc";
+        if (!write_goes(outname0, g1, args, nav0, (float)(g2.t - g1.t), zero.data(), zero.data(), zero.data(), zero.data(),
+                        zf.data(), zf.data(), args.doCTH == 1 ? z.data() : nullptr, &err))
+            return fail(err);
+        printf("%s written (dry run: no motion computed)\n", outname0.c_str());
+        return 0;
+    }
     octane_ctx* ctx = nullptr;
     int rc = octane_ctx_create(&ctx, args.setdevice);
     if (rc == OCTANE_ENODEV) { printf("No gpus available for use, exiting\n"); return 0; }      // .cu:1255-1259

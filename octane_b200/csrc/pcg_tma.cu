@@ -7,7 +7,7 @@
 // rows ahead, completion signalled on mbarriers.  The v1 kernel kept one row of
 // loads in flight per warp and sat at 25 % occupancy waiting on the long
 // scoreboard (profiles/r01_ncu_pass1_v1_conus.txt: 57 % of DRAM peak); here the
-// bytes in flight are set by the ring depth (5 rows x 45 KB per SM), not by
+// bytes in flight are set by the ring depth (4 rows x 45 KB per SM), not by
 // registers: a consumer warp copies what it needs of a staged row into registers
 // and hands the stage straight back to the producer.
 //
@@ -30,7 +30,10 @@ namespace {
 
 constexpr int SWMAX = 1024;                 // pixels per strip (256 consumer threads x 4)
 constexpr int HALO = 4;                     // floats of left halo (keeps 16-byte alignment)
-constexpr int NSTAGE = 5;                   // 5 x 45.3 KB = 226 KB of the SM's 227 KB
+#ifndef OCTANE_P1_NSTAGE
+#define OCTANE_P1_NSTAGE 4        // measured: 4 x 45.3 KB beats 5 (226 of the SM's 227 KB) by 1-3 %
+#endif
+constexpr int NSTAGE = OCTANE_P1_NSTAGE;
 constexpr int HA = SWMAX + 2 * HALO;        // floats per halo array
 constexpr int NHALO = 7, NCENTRE = 4;
 constexpr int STAGE_FLOATS = NHALO * HA + NCENTRE * SWMAX;

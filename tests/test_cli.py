@@ -1,0 +1,174 @@
+"""The `octane` host program (octane_b200/bin/octane): flag surface of reference src/main.cc, the
+self-contained classic-NetCDF reader/writer (octane_b200/csrc/cdf.cc) and, on a GPU, the whole
+path file -> ingest -> flow -> navigation -> outfile.nc against the library called directly."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+import goes_files as G
+import octane_b200 as ob
+from octane_b200 import synthetic as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "octane_b200", "bin", "octane")
+
+
+def run(*args, check=True):
+    r = subprocess.run([EXE, *args], capture_output=True, text=True, timeout=600)
+    if check:
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r
+
+
+def settings(*args):
+    out = run(*args, "-dump_settings").stdout
+    return dict(ln.split("=", 1) for ln in out.splitlines() if "=" in ln)
+
+
+def test_usage_and_defaults():
+    r = run()                                   # fewer than 3 arguments: usage text, exit 0 (src/main.cc:112-164)
+    assert "-i1 <filename>" in r.stdout and "-alpha" in r.stdout
+    s = settings()
+    # src/main.cc:53-108
+    assert (float(s["alpha"]), float(s["lambda"]), float(s["lambdac"]), float(s["scaleF"])) == (5.0, 1.0, 0.0, 0.5)
+    assert (int(s["kiters"]), int(s["liters"]), int(s["cgiters"]), int(s["miters"])) == (4, 3, 30, 5)
+    assert (int(s["dozim"]), int(s["oftype"]), int(s["pixuv"]), int(s["setdevice"])) == (1, 1, 0, 0)
+    assert all(int(s[k]) == 1 for k in ("outnav", "outraw", "outrad", "outctp", "interpcth"))
+
+
+def test_flags_and_reference_quirks():
+    s = settings("-i1", "a.nc", "-i2", "b.nc", "-alpha", "3.5", "-lambda", "0.25", "-lambdac", "0.1", "-kiters", "5", "-liters",
+                 "2", "-pd", "-brox", "-ir", "-i1cth", "c.nc", "-firstguess", "fg.nc", "-o", "/tmp/x/", "-set_device", "3",
+                 "-no_outraw", "-no_outctp", "-nncth", "-scsig", "7", "-cgiters", "99", "-corn")
+    assert (s["i1"], s["i2"], s["i1cth"], s["firstguess"], s["o"]) == ("a.nc", "b.nc", "c.nc", "fg.nc", "/tmp/x/")
+    assert (float(s["alpha"]), float(s["lambda"]), float(s["lambdac"])) == (3.5, 0.25, 0.1)
+    assert (int(s["kiters"]), int(s["liters"]), int(s["pixuv"]), int(s["ir"]), int(s["doCTH"])) == (5, 2, 1, 1, 1)
+    assert int(s["dozim"]) == 0 and int(s["oftype"]) == 3          # -brox: :265-268, :365-371
+    assert int(s["setdevice"]) == 2                                 # 1-based on the command line, :311-314
+    assert (int(s["outraw"]), int(s["outctp"]), int(s["outnav"]), int(s["interpcth"])) == (0, 0, 1, 0)
+    assert float(s["scsig"]) == 49.0                                # stores the square, :229
+    assert int(s["cgiters"]) == 30                                  # documented (:144) but never parsed
+    assert int(s["docorn"]) == 0                                    # -corn is a no-op, :270-273
+    assert int(settings("-Polar", "-i1cth", "c.nc")["doCTH"]) == 0  # :380-391
+    r = run("-i1", "a", "-i2", "b", "-farn")
+    assert "Farneback disabled" in r.stdout
+
+
+def _pair_files(tmp, nx=96, ny=80, band=2, cth=False, sector="meso_0.5km"):
+    c = dict(sector=sector, nx=nx, ny=ny, x0=10, y0=20)
+    xs, ys, xo, yo, dt = S.SECTORS[sector]
+    i1, i2, _, _ = S.make_pair(nx, ny, 21)
+    maxin, minin = ob.band_minmax(band)
+    radScale, radOffset = (maxin - minin) / 4000.0, minin
+    xc = (np.arange(nx) + c["x0"]).astype(np.int16); yc = (np.arange(ny) + c["y0"]).astype(np.int16)
+    f1, f2 = os.path.join(tmp, "g1.nc"), os.path.join(tmp, "g2.nc")
+    r1 = G.counts_from_image(i1, maxin, minin, radScale, radOffset); r2 = G.counts_from_image(i2, maxin, minin, radScale, radOffset)
+    G.write_goes_l1b(f1, r1, xc, yc, 1000.0, band, xs, xo, ys, yo, radScale, radOffset)
+    G.write_goes_l1b(f2, r2, xc, yc, 1000.0 + dt, band, xs, xo, ys, yo, radScale, radOffset)
+    return dict(f1=f1, f2=f2, r1=r1, r2=r2, xc=xc, yc=yc, dt=dt, xs=xs, ys=ys, xo=xo, yo=yo, radScale=radScale,
+                radOffset=radOffset, band=band, nx=nx, ny=ny)
+
+
+def test_netcdf_layout_matches_the_reference_writer(tmp_path):
+    """dry run (no GPU): read two GOES-shaped files, write outfile.nc; scipy must read it back and find
+    the reference's schema (src/oct_filewrite.cc:17-349): names, order, types, attributes."""
+    from scipy.io import netcdf_file
+    tmp = str(tmp_path)
+    d = _pair_files(tmp)
+    cth = (5000 + 4000 * np.sin(np.arange(d["nx"])[None, :] / 9.0) * np.ones((d["ny"], 1))).astype(np.float32)
+    G.write_plane_file(os.path.join(tmp, "cth.nc"), Cloud_Top_Height_Effective=cth)
+    run("-i1", d["f1"], "-i2", d["f2"], "-i1cth", os.path.join(tmp, "cth.nc"), "-o", tmp + "/", "-pd", "-dry_run")
+    f = netcdf_file(os.path.join(tmp, "outfile.nc"), "r", mmap=False)
+    assert list(f.dimensions.items()) == [("x", d["nx"]), ("y", d["ny"])]
+    want = ["x", "y", "t", "U", "V", "U_raw", "V_raw", "Upix", "Vpix", "CTP", "Rad", "goes_imager_projection",
+            "optical_flow_settings", "planck_fk1", "planck_fk2", "planck_bc1", "planck_bc2", "kappa0"]
+    assert list(f.variables) == want
+    v = f.variables
+    assert v["U"].dimensions == ("y", "x") and v["U"].data.dtype == np.dtype(">i2") and v["Upix"].data.dtype == np.dtype(">f4")
+    assert v["t"].data.dtype == np.dtype(">f8") and float(v["t"].getValue()) == 1000.0
+    assert v["U"].long_name == b"U" and v["U"].grid_mapping == b"goes_imager_projection" and v["U"].units == b"x-pixels"
+    assert v["V"].units == b"y-pixels" and abs(float(v["U"].scale_factor) - 0.01) < 1e-9
+    assert v["U_raw"].long_name == b"U Raw" and v["V_raw"].units == b"y-pixels"
+    assert np.array_equal(v["x"][:], d["xc"]) and np.array_equal(v["y"][:], d["yc"]) and np.array_equal(v["Rad"][:], d["r1"])
+    assert float(v["x"].scale_factor) == np.float32(d["xs"]) and float(v["y"].add_offset) == np.float32(d["yo"])
+    assert np.array_equal(v["CTP"][:], cth.astype(np.int16)) and float(v["CTP"].interpcth) == 1.0
+    g = v["goes_imager_projection"]
+    assert g.grid_mapping_name == b"geostationary" and g.sweep_angle_axis == b"x"
+    assert float(g.perspective_point_height) == float(np.float32(35786023.0)) and float(g.longitude_of_projection_origin) == -75.0
+    o = v["optical_flow_settings"]
+    assert int(o.getValue()) == 1 and int(o.K_Iterations) == 4 and int(o.L_Iterations) == 3 and int(o.CG_Iterations) == 30
+    assert float(o.alpha) == 5.0 and float(o.getattr("lambda") if hasattr(o, "getattr") else o.__dict__["_attributes"]["lambda"]) == 1.0
+    mx, mn = ob.band_minmax(2)
+    assert abs(float(o.NormMax) - mx) < 1e-4 and abs(float(o.NormMin) - mn) < 1e-5 and float(o.dt_seconds) == d["dt"]
+    assert float(o.Image2_xOffset) == np.float32(d["xo"])
+    assert abs(float(v["planck_fk1"].getValue()) - 202263.0) < 1e-2
+    f.close()
+    # without -pd / -i1cth the optional variables are absent; -no_out* drop their groups
+    run("-i1", d["f1"], "-i2", d["f2"], "-o", tmp + "/", "-no_outraw", "-no_outrad", "-dry_run")
+    f = netcdf_file(os.path.join(tmp, "outfile.nc"), "r", mmap=False)
+    assert list(f.variables) == ["x", "y", "t", "U", "V", "goes_imager_projection", "optical_flow_settings"]
+    assert f.variables["U"].units == b"meters per second"
+    f.close()
+
+
+def test_reader_rejects_what_it_cannot_read(tmp_path):
+    tmp = str(tmp_path)
+    bad = os.path.join(tmp, "hdf5.nc")
+    open(bad, "wb").write(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    r = run("-i1", bad, "-i2", bad, "-dry_run", check=False)
+    assert r.returncode == 1 and "classic format only" in r.stderr
+    r = run("-i1", os.path.join(tmp, "missing.nc"), "-i2", bad, "-dry_run", check=False)
+    assert r.returncode == 1 and "cannot open" in r.stderr
+    d = _pair_files(tmp)
+    G.write_plane_file(os.path.join(tmp, "cth_small.nc"), Cloud_Top_Height_Effective=np.zeros((10, 12), np.float32))
+    r = run("-i1", d["f1"], "-i2", d["f2"], "-i1cth", os.path.join(tmp, "cth_small.nc"), "-dry_run", check=False)
+    assert r.returncode == 1 and "regridding" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["default", "pd_cth", "firstguess"])
+def test_cli_end_to_end_matches_the_library(tmp_path, ctx, mode):
+    """file -> octane -> outfile.nc equals ingest + flow + navigation called through the C ABI"""
+    from scipy.io import netcdf_file
+    tmp = str(tmp_path)
+    d = _pair_files(tmp, nx=160, ny=128)
+    nx, ny = d["nx"], d["ny"]
+    args = ["-i1", d["f1"], "-i2", d["f2"], "-o", tmp + "/"]
+    p = ob.default_params()
+    cth = None
+    u0 = np.zeros((ny, nx), np.float32); v0 = np.zeros((ny, nx), np.float32)
+    nav = ob.goes_nav(d["xs"], d["ys"], d["xo"], d["yo"], pph=float(np.float32(35786023.0)), req=float(np.float32(6378137.0)),
+                      rpol=float(np.float32(6356752.31414)))
+    nav.lam0 = float(np.float32(np.float32(-75.0) * (3.14159265359 / 180.)))
+    cal = ob.goes_cal(d["radScale"], d["radOffset"], band=d["band"], fk1=202263.0, fk2=3698.19, bc1=0.43361, bc2=0.99939,
+                      kap1=0.0019486)
+    img1, lat, lon = ctx.oct_navcal_cuda(d["r1"], d["xc"], d["yc"], nav, cal)
+    cal.donav = 0
+    img2, _, _ = ctx.oct_navcal_cuda(d["r2"], d["xc"], d["yc"], nav, cal)
+    if mode == "pd_cth":
+        cth = (6000 + 5000 * np.cos(np.arange(nx)[None, :] / 11.0) * np.ones((ny, 1))).astype(np.float32)
+        G.write_plane_file(os.path.join(tmp, "cth.nc"), Cloud_Top_Height_Effective=cth)
+        args += ["-pd", "-i1cth", os.path.join(tmp, "cth.nc"), "-alpha", "8", "-kiters", "3"]
+        p = ob.default_params(pixuv=1, doCTH=1, alpha=8.0, kiters=3)
+    if mode == "firstguess":
+        ufg, vfg = cases.uv2pix_winds(nx, ny)
+        G.write_plane_file(os.path.join(tmp, "fg.nc"), UFG=ufg, VFG=vfg)
+        args += ["-firstguess", os.path.join(tmp, "fg.nc"), "-lambdac", "0.5"]
+        p = ob.default_params(first_guess=1, lambdac=0.5)
+        u0, v0 = ufg.copy(), vfg.copy()
+        ctx.oct_uv2pix(nav, 1000.0, 1000.0 + d["dt"], lat, lon, d["xc"], d["yc"], u0, v0, p)
+    run(*args)
+    want = ctx.oct_optical_flow(img1, img2, nav, 1000.0, 1000.0 + d["dt"], p, cth=cth, upix=u0, vpix=v0)
+    f = netcdf_file(os.path.join(tmp, "outfile.nc"), "r", mmap=False)
+    v = f.variables
+    for name, key in (("U", "uVal"), ("V", "vVal"), ("U_raw", "uVal2"), ("V_raw", "vVal2")):
+        assert np.array_equal(v[name][:], want[key]), name
+    if mode == "pd_cth":
+        assert np.array_equal(v["Upix"][:], want["uPix"]) and np.array_equal(v["Vpix"][:], want["vPix"])
+        assert np.array_equal(v["CTP"][:], want["CTP"]) and int(v["optical_flow_settings"].K_Iterations) == 3
+    assert int(v["optical_flow_settings"].dofirstguess) == int(mode == "firstguess")
+    assert np.abs(v["U_raw"][:].astype(int)).max() > 20        # a real flow field came out (>0.2 px)
+    f.close()
