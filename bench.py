@@ -330,9 +330,10 @@ def main():
     launches = int(st.kernel_launches)
     mpix = nx * ny / 1e6
 
-    # ---- end to end through the host-buffer C-ABI entry point (N = 1) or its band equivalent
-    e2e = None
-    if not args.no_e2e:
+    # ---- end to end through the host-buffer C-ABI entry point (N = 1) or its band equivalent.
+    # A function of its own: the pinned buffers must be released while the context's stream is still
+    # alive (torch's host allocator records an event on every stream a pinned block was used on).
+    def run_e2e():
         if world == 1:
             h1 = torch.empty((ny, nx), dtype=torch.float32, pin_memory=True); h1.copy_(img1)
             h2 = torch.empty((ny, nx), dtype=torch.float32, pin_memory=True); h2.copy_(img2)
@@ -369,15 +370,32 @@ def main():
         for _ in range(min(args.warmup, 1)):
             e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
-        e2e = {"value": mpix / (ms_e2e / 1e3), "unit": "Mpix/s", "ms_per_step": ms_e2e,
+        res = {"value": mpix / (ms_e2e / 1e3), "unit": "Mpix/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "api": "octane_optical_flow (host buffers, pinned)" if world == 1 else
                       "pinned band H2D + octane_variational_flow_band_dev + octane_pix2uv_band_dev + D2H"}
-        del h1, h2
+        return res
 
-    if rank != 0:
+
+    e2e = None if args.no_e2e else run_e2e()
+    torch.cuda.synchronize()
+
+    def shutdown():
+        # every rank's kernels are done before anybody frees memory a neighbour has mapped
+        ctx.synchronize()
+        if dist:
+            dist.barrier()
+        ctx.close()
         if dist:
             dist.destroy_process_group()
+            # multi-process runs: skip interpreter finalisation, where torch / NCCL / CUDA-IPC objects
+            # are torn down in no particular order (seen as "context is destroyed" aborts after the result line)
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        del img1, img2, u, v, shorts
+        shutdown()
         return
 
     # ---- roofline of the dominant kernel (finest-level PCG passes, timed live above)
@@ -428,8 +446,8 @@ def main():
         except Exception as e:
             line["ref_cuda_sm100"] = {"unavailable": str(e)[:120]}
     print(json.dumps(line), flush=True)
-    if dist:
-        dist.destroy_process_group()
+    del img1, img2, u, v, shorts
+    shutdown()
 
 
 if __name__ == "__main__":

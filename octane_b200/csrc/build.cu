@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(1024) k_build_finish(PcgBuffers b, unsigned nb
         acc[1] += b.partials[(size_t)nblocks + i];
     }
     block_sum<2>(acc, red);
+    if (b.p2p.world > 1) p2p_allreduce<2>(b.p2p, P2P_BUILD, acc, &b.scal->comm_err);
     if (threadIdx.x == 0 && b.defer) {
         b.pending[0] = acc[0];
         b.pending[1] = acc[1];

@@ -7,6 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 namespace octane {
 
 namespace {
@@ -18,6 +20,7 @@ struct Api {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -42,7 +45,7 @@ bool load()
     *(void**)(&api.field) = dlsym(h, name); \
     if (!api.field) { snprintf(errbuf, sizeof errbuf, "libnccl lacks %s", name); return false; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-    SYM(AllReduce, "ncclAllReduce") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+    SYM(AllReduce, "ncclAllReduce") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllGather, "ncclAllGather")
     SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     api.h = h;
@@ -82,8 +85,112 @@ int comm_init(Comm* c, const char id[128], int rank, int world)
     return 0;
 }
 
+namespace {
+
+// every rank contributes `bytes` bytes; out (host) receives world * bytes
+int allgather_bytes(Comm* c, const void* mine, size_t bytes, void* out, cudaStream_t st)
+{
+    char* d = nullptr;
+    if (cudaMalloc(&d, bytes * (c->world + 1)) != cudaSuccess) { snprintf(errbuf, sizeof errbuf, "cudaMalloc (allgather)"); return -1; }
+    int rc = 0;
+    if (cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
+    if (!rc) rc = check(api.AllGather(d, d + bytes, bytes, ncclChar, (ncclComm_t)c->nccl_comm, st), "ncclAllGather");
+    if (!rc && cudaMemcpyAsync(out, d + bytes, bytes * c->world, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = -1;
+    if (rc && !errbuf[0]) snprintf(errbuf, sizeof errbuf, "allgather of IPC handles failed");
+    cudaFree(d);
+    return rc;
+}
+
+// min over ranks of a flag: do all ranks agree that a step worked?
+int all_ok(Comm* c, int ok, cudaStream_t st)
+{
+    std::vector<int> flags(c->world, 0);
+    if (allgather_bytes(c, &ok, sizeof ok, flags.data(), st)) return -1;
+    for (int f : flags) if (!f) return 0;
+    return 1;
+}
+
+}  // namespace
+
+int comm_p2p_init(Comm* c, size_t window_bytes, cudaStream_t st)
+{
+    c->p2p = false;
+    if (c->world <= 1 || c->world > 16) return 0;
+    const char* mode = getenv("OCTANE_COMM");
+    if (mode && !strcmp(mode, "nccl")) return 0;           // developer switch: per-iteration exchanges over NCCL
+    int ok = 1;
+    if (cudaMalloc(&c->window, window_bytes) != cudaSuccess || cudaMemset(c->window, 0, window_bytes) != cudaSuccess) ok = 0;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok && cudaIpcGetMemHandle(&mine, c->window) != cudaSuccess) ok = 0;
+    std::vector<cudaIpcMemHandle_t> all(c->world);
+    if (allgather_bytes(c, &mine, sizeof mine, all.data(), st)) return -1;
+    for (int r = 0; r < c->world && ok; r++) {
+        if (r == c->rank) { c->peer_window[r] = c->window; continue; }
+        if (cudaIpcOpenMemHandle(&c->peer_window[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            c->peer_window[r] = nullptr;
+            ok = 0;
+        }
+    }
+    if (ok) {
+        if (cudaMalloc(&c->d_peers, sizeof(void*) * 16) != cudaSuccess ||
+            cudaMemcpy(c->d_peers, c->peer_window, sizeof(void*) * 16, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMalloc(&c->d_epoch, 4 * sizeof(unsigned)) != cudaSuccess ||
+            cudaMemset(c->d_epoch, 0, 4 * sizeof(unsigned)) != cudaSuccess)
+            ok = 0;
+    }
+    const int agreed = all_ok(c, ok, st);                  // also a barrier: every window is zeroed and mapped
+    if (agreed < 0) return -1;
+    c->p2p = agreed == 1;
+    return 0;
+}
+
+int comm_p2p_unmap_arenas(Comm* c, cudaStream_t st)
+{
+    if (!c->p2p) return 0;
+    for (int k = 0; k < 2; k++) {
+        if (c->nb_arena[k]) cudaIpcCloseMemHandle(c->nb_arena[k]);
+        c->nb_arena[k] = nullptr;
+    }
+    return all_ok(c, 1, st) < 0 ? -1 : 0;                  // barrier: nobody frees a workspace a peer still maps
+}
+
+int comm_p2p_map_arenas(Comm* c, void* my_arena, cudaStream_t st)
+{
+    if (!c->p2p) return 0;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    int ok = cudaIpcGetMemHandle(&mine, my_arena) == cudaSuccess;
+    std::vector<cudaIpcMemHandle_t> all(c->world);
+    if (allgather_bytes(c, &mine, sizeof mine, all.data(), st)) return -1;
+    const int nb[2] = { c->rank - 1, c->rank + 1 };
+    for (int k = 0; k < 2 && ok; k++) {
+        if (nb[k] < 0 || nb[k] >= c->world) continue;
+        if (cudaIpcOpenMemHandle(&c->nb_arena[k], all[nb[k]], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            c->nb_arena[k] = nullptr;
+            ok = 0;
+        }
+    }
+    const int agreed = all_ok(c, ok, st);
+    if (agreed < 0) return -1;
+    if (agreed == 0) { snprintf(errbuf, sizeof errbuf, "a rank could not map its neighbour's workspace (CUDA IPC)"); return -1; }
+    return 0;
+}
+
 void comm_destroy(Comm* c)
 {
+    for (int k = 0; k < 2; k++) { if (c->nb_arena[k]) cudaIpcCloseMemHandle(c->nb_arena[k]); c->nb_arena[k] = nullptr; }
+    for (int r = 0; r < 16; r++) {
+        if (c->peer_window[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_window[r]);
+        c->peer_window[r] = nullptr;
+    }
+    if (c->window) cudaFree(c->window);
+    if (c->d_peers) cudaFree(c->d_peers);
+    if (c->d_epoch) cudaFree(c->d_epoch);
+    c->window = nullptr; c->d_peers = nullptr; c->d_epoch = nullptr; c->p2p = false;
     if (c->nccl_comm && api.CommDestroy) api.CommDestroy((ncclComm_t)c->nccl_comm);
     c->nccl_comm = nullptr;
     c->world = 1;

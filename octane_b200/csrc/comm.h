@@ -13,6 +13,14 @@ namespace octane {
 struct Comm {
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
+    // peer-memory path (CUDA IPC over NVLink; common.cuh: P2PWindow).  NCCL stays for the bootstrap
+    // and for the per-solve u,v halo rows; the per-iteration dots and r rows go through these.
+    bool p2p = false;
+    void* window = nullptr;              // this rank's window (device memory, zeroed)
+    void* peer_window[16] = { nullptr }; // every rank's window as mapped here ([rank] = window)
+    void** d_peers = nullptr;            // device copy of peer_window
+    unsigned* d_epoch = nullptr;         // device [3]
+    void* nb_arena[2] = { nullptr, nullptr };   // rank-1 / rank+1 workspace as mapped here
 };
 
 int comm_unique_id(char id[128]);
@@ -25,6 +33,14 @@ int comm_allreduce_f64(Comm* c, double* d_buf, int n, cudaStream_t st);
 // neighbours' counterparts into recv_up[p] (from rank-1) and recv_dn[p] (from rank+1).
 int comm_halo_exchange(Comm* c, int nplanes, float* const* send_up, float* const* recv_up,
                        float* const* send_dn, float* const* recv_dn, size_t count, cudaStream_t st);
+// After comm_init: allocate the window, exchange IPC handles (ncclAllGather), map the peers.  Returns 0
+// and sets c->p2p = true when every rank succeeded; 0 with p2p = false when any rank could not map
+// its peers (the NCCL path is used); -1 on a hard error.
+int comm_p2p_init(Comm* c, size_t window_bytes, cudaStream_t st);
+// Collective, call when the workspace (re)appears: unmap the neighbours' old workspaces
+// (comm_p2p_unmap_arenas, before anybody frees), then map the new ones.
+int comm_p2p_unmap_arenas(Comm* c, cudaStream_t st);
+int comm_p2p_map_arenas(Comm* c, void* my_arena, cudaStream_t st);
 const char* comm_last_error();
 
 }  // namespace octane

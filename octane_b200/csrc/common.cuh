@@ -33,7 +33,55 @@ struct PcgScalars {
     int done;       // stop rule satisfied: !(rr > tol)
     int its;        // iterations executed in this solve
     int halo_err;   // banded runs: warp left the local rows
+    int comm_err;   // banded runs: a peer's contribution did not arrive in time
 };
+
+// ---- peer-memory exchange between the row bands (one process per GPU) -----------------------
+// Every rank owns one small window in device memory that all its peers have mapped (CUDA IPC over
+// NVLink).  A grid-wide dot product becomes a cross-GPU one inside the same kernel: the last block
+// stores this rank's partial straight into every peer's window, releases a sequence number, waits
+// for the peers' numbers in its own window and sums the partials in rank order -- the same bits on
+// every rank, so the bands take the same stop decision without a host or an NCCL call in between.
+// Phases alternate (build / pass 1 / pass 2) and values are double-buffered on the epoch's parity,
+// so a rank that runs ahead can never overwrite a value a slower peer still has to read.
+constexpr int P2P_MAXW = 16;
+enum { P2P_BUILD = 0, P2P_PASS1 = 1, P2P_PASS2 = 2, P2P_NPHASE = 3 };
+struct P2PWindow {
+    double val[P2P_NPHASE][2][P2P_MAXW][2];
+    unsigned seq[P2P_NPHASE][2][P2P_MAXW];
+};
+struct P2P {
+    int world, rank;              // world <= 1: disabled
+    P2PWindow* const* peers;      // device array [world]: every rank's window as mapped here (peers[rank] = own)
+    unsigned* epoch;              // device [P2P_NPHASE], advanced by the publishing block
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(double* p, double v)
+{
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // clamp-to-edge on a global index (oct_bc_cu, :26-41, on integer-valued floats)
 __device__ __forceinline__ int clampi(int x, int n) { return x < 0 ? 0 : (x >= n ? n - 1 : x); }
@@ -81,7 +129,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* NV*32
 // in out[] (valid in thread 0).
 template <int NV>
 __device__ __forceinline__ bool grid_sum_finish(const double (&mine)[NV], double* partials, unsigned* ticket,
-                                                double (&out)[NV], double* smem)
+                                                double (&out)[NV], double* smem, bool sys_fence = false)
 {
     __shared__ bool is_last;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -91,7 +139,8 @@ __device__ __forceinline__ bool grid_sum_finish(const double (&mine)[NV], double
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < NV; k++) partials[(size_t)k * nblocks + bid] = mine[k];
-        __threadfence();
+        if (sys_fence) __threadfence_system();      // the block stored into a peer GPU's memory
+        else __threadfence();
         unsigned t = atomicAdd(ticket, 1u);
         is_last = (t == nblocks - 1);
     }
@@ -108,6 +157,49 @@ __device__ __forceinline__ bool grid_sum_finish(const double (&mine)[NV], double
     block_sum<NV>(out, smem);
     if (tid == 0) *ticket = 0u;
     return true;
+}
+
+
+// Cross-rank sum of NV doubles held by thread 0 of the calling block (the last block of a grid, after
+// grid_sum_finish).  All threads of the block must call it; the totals come back in thread 0.  A peer
+// that does not answer within 10 s sets *comm_err and the call returns what it has (the host turns
+// the flag into OCTANE_ECOMM; nothing spins for ever).
+template <int NV>
+__device__ __forceinline__ void p2p_allreduce(const P2P& c, int phase, double (&tot)[NV], int* comm_err)
+{
+    __shared__ double s_val[NV];
+    __shared__ unsigned s_epoch;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid == 0) {
+        const unsigned e = c.epoch[phase] + 1u;
+        c.epoch[phase] = e;
+        s_epoch = e;
+#pragma unroll
+        for (int k = 0; k < NV; k++) s_val[k] = tot[k];
+    }
+    __syncthreads();
+    const unsigned e = s_epoch;
+    const int par = (int)(e & 1u);
+    P2PWindow* mine = c.peers[c.rank];
+    if (tid < c.world) {
+        P2PWindow* w = c.peers[tid];
+#pragma unroll
+        for (int k = 0; k < NV; k++) st_relaxed_sys(&w->val[phase][par][c.rank][k], s_val[k]);
+        st_release_sys(&w->seq[phase][par][c.rank], e);
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(&mine->seq[phase][par][tid]) != e) {
+            if (global_ns() - t0 > 10000000000ull) { atomicExch(comm_err, 1); break; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double s = 0.0;
+            for (int r = 0; r < c.world; r++) s += ld_relaxed_sys(&mine->val[phase][par][r][k]);
+            tot[k] = s;
+        }
+    }
 }
 
 }  // namespace octane

@@ -66,6 +66,9 @@ struct Level {
     int own0, own1;          // rows this rank solves
     Geom g;                  // local storage
     float lambdac;
+    // peer-memory runs: the neighbours' r planes, shifted so that p[g.at(i, j)] with THIS rank's
+    // geometry addresses (i, j) in the neighbour's plane (nullptr at the outer edges)
+    float *up_ru = nullptr, *up_rv = nullptr, *dn_ru = nullptr, *dn_rv = nullptr;
 };
 
 struct Plan {
@@ -259,6 +262,12 @@ int prepare(octane_ctx* c, int nx, int ny, int nc, const octane_params& p)
     int rc = make_plan(pl, nx, ny, nc, p, c->comm.rank, c->comm.world);
     if (rc) return rc;
     const size_t need = arena_layout(pl, nullptr, nullptr);
+    const bool p2p = c->comm.world > 1 && c->comm.p2p;
+    if (p2p) {
+        // collective (every rank re-plans at the same call): nobody may free a workspace a peer still maps
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (comm_p2p_unmap_arenas(&c->comm, c->stream)) { set_err("%s", comm_last_error()); return OCTANE_ECOMM; }
+    }
     if (need > c->arena_bytes) {
         CUDA_OK(cudaStreamSynchronize(c->stream));
         if (c->arena) cudaFree(c->arena);
@@ -270,6 +279,24 @@ int prepare(octane_ctx* c, int nx, int ny, int nc, const octane_params& p)
     // coefficients): clear the whole workspace once per plan
     CUDA_OK(cudaMemsetAsync(c->arena, 0, need, c->stream));
     arena_layout(pl, &c->buf, c->arena);
+    if (p2p) {
+        CUDA_OK(cudaStreamSynchronize(c->stream));           // the clear must not race a neighbour's first halo store
+        if (comm_p2p_map_arenas(&c->comm, c->arena, c->stream)) { set_err("%s", comm_last_error()); return OCTANE_ECOMM; }
+        for (int side = 0; side < 2; side++) {
+            const int nb = c->comm.rank + (side == 0 ? -1 : 1);
+            if (nb < 0 || nb >= c->comm.world) continue;
+            Plan pn;
+            rc = make_plan(pn, nx, ny, nc, p, nb, c->comm.world);
+            if (rc) return rc;
+            Buffers bn;
+            arena_layout(pn, &bn, (char*)c->comm.nb_arena[side]);
+            for (size_t k = 0; k < pl.lv.size(); k++) {
+                const long long shift = (long long)(pl.lv[k].g.j0 - pn.lv[k].g.j0) * pl.lv[k].g.pitch;
+                if (side == 0) { pl.lv[k].up_ru = bn.pcg.ru + shift; pl.lv[k].up_rv = bn.pcg.rv + shift; }
+                else { pl.lv[k].dn_ru = bn.pcg.ru + shift; pl.lv[k].dn_rv = bn.pcg.rv + shift; }
+            }
+        }
+    }
     int pb = c->sm_count * 16;
     const Level& F = pl.lv.back();
     int bb = build_partial_blocks(F.g, F.g.rows);
@@ -282,7 +309,12 @@ int prepare(octane_ctx* c, int nx, int ny, int nc, const octane_params& p)
     c->buf.pcg.ticket = c->d_ticket;
     c->buf.pcg.max_partial_blocks = c->partial_blocks;
     c->buf.pcg.pending = c->d_pending;
-    c->buf.pcg.defer = (c->comm.world > 1) ? 1 : 0;
+    c->buf.pcg.defer = (c->comm.world > 1 && !p2p) ? 1 : 0;
+    c->buf.pcg.p2p.world = p2p ? c->comm.world : 1;
+    c->buf.pcg.p2p.rank = c->comm.rank;
+    c->buf.pcg.p2p.peers = (P2PWindow* const*)c->comm.d_peers;
+    c->buf.pcg.p2p.epoch = c->comm.d_epoch;
+    c->buf.pcg.up_ru = c->buf.pcg.up_rv = c->buf.pcg.dn_ru = c->buf.pcg.dn_rv = nullptr;
     c->plan = pl;
     c->pcg_graph.assign(pl.lv.size(), nullptr);
     c->plan_valid = true;
@@ -348,9 +380,14 @@ int allreduce_pending(octane_ctx* c, int n)
 // ---- the PCG loop of one solve (:1129-1182), enqueued or captured ----------------------
 int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve)
 {
-    const PcgBuffers& b = c->buf.pcg;
+    PcgBuffers b = c->buf.pcg;
     const int iters = c->plan.p.cgiters;
     const bool multi = c->comm.world > 1;
+    const bool p2p = multi && c->comm.p2p;
+    // peer-memory runs: pass 2 stores its boundary rows of r straight into the neighbours' halo rows
+    // and the last block of each pass sums the dots across the ranks itself (2 launches per iteration,
+    // as on one GPU); otherwise NCCL: all-reduce + a scalar kernel after each pass, send/recv of r
+    if (p2p) { b.up_ru = L.up_ru; b.up_rv = L.up_rv; b.dn_ru = L.dn_ru; b.dn_rv = L.dn_rv; }
     for (int ki = 0; ki < iters; ki++) {
         {
             Scope s(c, CAT_P1, level, solve, ki);
@@ -360,7 +397,7 @@ int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve)
                 launch_pcg_pass1(b, L.g, L.own0, L.own1, ki, multi, c->sm_count, c->stream);
             c->launches++;
         }
-        if (multi) {
+        if (multi && !p2p) {
             int rc = allreduce_pending(c, 1); if (rc) return rc;
             launch_finalize(b, FINALIZE_PASS1, 0.f, c->stream); c->launches++;
         }
@@ -369,7 +406,7 @@ int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve)
             launch_pcg_pass2(b, L.g, L.own0, L.own1, c->sm_count, c->stream);
             c->launches++;
         }
-        if (multi) {
+        if (multi && !p2p) {
             int rc = allreduce_pending(c, 2); if (rc) return rc;
             launch_finalize(b, FINALIZE_PASS2, 0.f, c->stream); c->launches++;
             float* planes[2] = { b.ru, b.rv };            // next pass 1 rebuilds p on the halo rows from r
@@ -399,7 +436,7 @@ int run_pcg(octane_ctx* c, const Level& L, int level, int solve)
         c->pcg_graph[level] = exec;
     }
     CUDA_OK(cudaGraphLaunch(c->pcg_graph[level], c->stream));
-    c->launches += (long long)c->plan.p.cgiters * (c->comm.world > 1 ? 4 : 2);
+    c->launches += (long long)c->plan.p.cgiters * ((c->comm.world > 1 && !c->comm.p2p) ? 4 : 2);
     return OCTANE_OK;
 }
 
@@ -482,7 +519,7 @@ int run_levels(octane_ctx* c)
                     Scope s(c, CAT_BUILD, k, solve);
                     launch_build(f, B.pcg, g, ba, bb, L.own0, L.own1, bp, multi ? 1 : 0, st);
                     c->launches += 2;
-                    if (multi) {
+                    if (multi && !c->comm.p2p) {
                         int rc = allreduce_pending(c, 2); if (rc) return rc;
                         launch_finalize(B.pcg, FINALIZE_BUILD, bp.tol, st); c->launches++;
                     }
@@ -796,6 +833,7 @@ int octane_variational_flow_band_dev(octane_ctx* c, const float* d_img1, const f
     if (c->comm.world > 1) {          // halo check needs the device flag
         CUDA_OK(cudaStreamSynchronize(c->stream));
         if (c->h_scal->halo_err) { set_err("warp left the band halo: raise max_disp"); return OCTANE_EHALO; }
+        if (c->h_scal->comm_err) { set_err("a peer's partial sums did not arrive (peer-memory exchange timed out)"); return OCTANE_ECOMM; }
     }
     return OCTANE_OK;
 }
@@ -1088,6 +1126,8 @@ int octane_comm_init(octane_ctx* c, const char id[128], int rank, int world)
     comm_destroy(&c->comm);
     if (world == 1) return OCTANE_OK;
     if (comm_init(&c->comm, id, rank, world)) { set_err("%s", comm_last_error()); return OCTANE_ECOMM; }
+    // per-iteration exchanges over peer memory when every rank can map its peers (else NCCL)
+    if (comm_p2p_init(&c->comm, sizeof(P2PWindow), c->stream)) { set_err("%s", comm_last_error()); return OCTANE_ECOMM; }
     return OCTANE_OK;
 }
 

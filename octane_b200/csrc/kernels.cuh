@@ -38,8 +38,13 @@ struct PcgBuffers {
     unsigned* ticket;          // device
     int max_partial_blocks;
     double* pending;           // device [2]: rank-local dot totals awaiting the all-reduce
-    int defer;                 // 1 (banded runs): kernels leave totals in `pending`;
+    int defer;                 // 1 (banded runs over NCCL): kernels leave totals in `pending`;
                                // launch_finalize applies them after the all-reduce
+    P2P p2p;                   // banded runs over peer memory (world > 1): the kernels' last block
+                               // exchanges the totals itself and finalises as on one GPU
+    // pass 2 pushes its boundary rows of r into the neighbours' halo rows (peer memory); the
+    // pointers are pre-shifted so that p[g.at(i, j)] with THIS rank's geometry lands on (i, j) there
+    float *up_ru, *up_rv, *dn_ru, *dn_rv;
 };
 enum { FINALIZE_BUILD = 0, FINALIZE_PASS1 = 1, FINALIZE_PASS2 = 2 };
 void launch_finalize(const PcgBuffers& b, int kind, float tol, cudaStream_t st);

@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(256, 2) k_pcg_pass1(P1Args a)
     block_sum<1>(dot, red);
     double tot[1];
     if (grid_sum_finish<1>(dot, a.b.partials, a.b.ticket, tot, red)) {
+        if (a.b.p2p.world > 1) p2p_allreduce<1>(a.b.p2p, P2P_PASS1, tot, &a.b.scal->comm_err);
         if (threadIdx.x == 0) {
             if (a.b.defer) a.b.pending[0] = tot[0];
             else a.b.scal->pAp = (float)tot[0];                        // pkTApk, :1165
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(256) k_pcg_pass2(P2Args a)
     const float alphak = s->rz / s->pAp;                      // :1169
     const float nalpha = -1. * alphak;                        // :1174
     const Geom& g = a.g;
+    const bool p2p = a.b.p2p.world > 1;
     const int upr = g.pitch >> 2;                             // float4 units per row
     const long long nunits = (long long)(a.jb - a.ja) * upr;
     double acc[2] = { 0.0, 0.0 };
@@ -265,12 +267,20 @@ __global__ void __launch_bounds__(256) k_pcg_pass2(P2Args a)
         }
         st4(a.b.ru + off, r_u);
         st4(a.b.rv + off, r_v);
+        if (p2p) {
+            // the band's first / last owned row is the neighbour's halo row: store it there as well
+            // (peer memory over NVLink), so the next pass 1 rebuilds p on the halo without an exchange step
+            const int j = a.ja + jr;
+            if (j == a.ja && a.b.up_ru) { st4(a.b.up_ru + off, r_u); st4(a.b.up_rv + off, r_v); __threadfence_system(); }
+            if (j == a.jb - 1 && a.b.dn_ru) { st4(a.b.dn_ru + off, r_u); st4(a.b.dn_rv + off, r_v); __threadfence_system(); }
+        }
         acc[0] += (double)prr;
         acc[1] += (double)prz;
     }
     block_sum<2>(acc, red);
     double tot[2];
-    if (grid_sum_finish<2>(acc, a.b.partials, a.b.ticket, tot, red)) {
+    if (grid_sum_finish<2>(acc, a.b.partials, a.b.ticket, tot, red, p2p)) {
+        if (p2p) p2p_allreduce<2>(a.b.p2p, P2P_PASS2, tot, &a.b.scal->comm_err);
         if (threadIdx.x == 0 && a.b.defer) {
             a.b.pending[0] = tot[0];
             a.b.pending[1] = tot[1];

@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(SWMAX / PX + 32, 1) k_pcg_pass1_tma(TArgs a)
     block_sum<1>(dot, red);
     double tot[1];
     if (grid_sum_finish<1>(dot, a.b.partials, a.b.ticket, tot, red)) {
+        if (a.b.p2p.world > 1) p2p_allreduce<1>(a.b.p2p, P2P_PASS1, tot, &a.b.scal->comm_err);
         if (threadIdx.x == 0) {
             if (a.b.defer) a.b.pending[0] = tot[0];
             else a.b.scal->pAp = (float)tot[0];
