@@ -29,6 +29,9 @@
  *   octane_uv2pix*             void oct_uv2pix(GOESVar&,float*u,float*v,double t2,OFFlags)
  *                              src/oct_pix2uv_cuda.cu:372 (first-guess winds -> pixel displacements)
  *   octane_band_minmax         void oct_bandminmax(int,float&,float&), src/oct_normalize_geo.cc:9
+ *   octane_zoom_in_float       void oct_zoom_in_float(float*flow,float*flowout,int nx,int ny,int nxx,int nyy,
+ *                              int cnum,int interp), src/oct_zoom.cc:180 (cloud-top heights / extra channels
+ *                              on a coarser grid, src/oct_fileread.cc:370,796)
  * Image layout everywhere: row-major float32, index i + nx*j (+ nx*ny*c), i = x
  * (fastest), as the reference (src/oct_variational_optical_flow.cu:316-320).
  */
@@ -178,6 +181,10 @@ int octane_uv2pix(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
                   const float* lat, const float* lon, const short* x, const short* y,
                   int nx, int ny, const octane_params* p, float* u_inout, float* v_inout);
 
+/* Regrid a coarser ancillary field (nx*ny) onto the image grid (nxx*nyy >= nx*ny): bicubic when
+ * interp == 1 (default of the reference, -nncth selects 0 = nearest neighbour). */
+int octane_zoom_in_float(octane_ctx* ctx, const float* in, int nx, int ny, float* out, int nxx, int nyy, int interp);
+
 /* ---- device-pointer entry points (stream-ordered on the ctx stream) ----- */
 /* All pointers are device memory on the context's device, dense (stride nx). */
 int octane_variational_flow_dev(octane_ctx* ctx, const float* d_img1, const float* d_img2,
@@ -189,6 +196,7 @@ int octane_pix2uv_dev(octane_ctx* ctx, const octane_nav* nav, double t1, double 
 
 int octane_navcal_dev(octane_ctx* ctx, const short* d_rad, const short* d_x, const short* d_y, int nx, int ny,
                       const octane_nav* nav, const octane_cal* cal, float* d_data, float* d_lat, float* d_lon);
+int octane_zoom_in_float_dev(octane_ctx* ctx, const float* d_in, int nx, int ny, float* d_out, int nxx, int nyy, int interp);
 int octane_uv2pix_dev(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
                       const float* d_lat, const float* d_lon, const short* d_x, const short* d_y,
                       int nx, int ny, const octane_params* p, float* d_u_inout, float* d_v_inout);

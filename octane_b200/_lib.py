@@ -62,6 +62,7 @@ EXPORTS = [
     "octane_variational_flow", "octane_pix2uv", "octane_optical_flow",
     "octane_variational_flow_dev", "octane_pix2uv_dev",
     "octane_navcal", "octane_navcal_dev", "octane_band_minmax", "octane_uv2pix", "octane_uv2pix_dev",
+    "octane_zoom_in_float", "octane_zoom_in_float_dev",
     "octane_stage_blur_decimate", "octane_stage_gradient", "octane_stage_zoom_in",
     "octane_stage_build", "octane_stage_pcg",
     "octane_band_plan", "octane_comm_unique_id", "octane_comm_init", "octane_comm_rank",
@@ -110,6 +111,8 @@ def load() -> C.CDLL:
     L.octane_band_minmax.argtypes = [i, fp, fp]
     L.octane_uv2pix.argtypes = [vp, NP, d, d, vp, vp, vp, vp, i, i, PP, vp, vp]
     L.octane_uv2pix_dev.argtypes = [vp, NP, d, d, vp, vp, vp, vp, i, i, PP, vp, vp]
+    L.octane_zoom_in_float.argtypes = [vp, vp, i, i, vp, i, i, i]
+    L.octane_zoom_in_float_dev.argtypes = [vp, vp, i, i, vp, i, i, i]
     L.octane_stage_blur_decimate.argtypes = [vp, vp, i, i, i, f, vp]
     L.octane_stage_gradient.argtypes = [vp, vp, i, i, i, vp, vp]
     L.octane_stage_zoom_in.argtypes = [vp, vp, i, i, i, i, f, vp]

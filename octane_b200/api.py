@@ -290,6 +290,20 @@ class Context:
                                           _ptr(data), _ptr(lat), _ptr(lon)))
         return data, lat, lon
 
+    def oct_zoom_in_float(self, field, nxx: int, nyy: int, interp: int = 1):
+        """regrid a coarser field onto an nyy x nxx grid (oct_zoom_in_float, src/oct_zoom.cc:180)"""
+        ny, nx = field.shape
+        if _is_torch(field):
+            import torch
+            out = torch.empty((nyy, nxx), dtype=torch.float32, device=field.device)
+            self._after_torch()
+            self._check(self._L.octane_zoom_in_float_dev(self._h, _ptr(field), nx, ny, _ptr(out), nxx, nyy, interp))
+            return out
+        field = np.ascontiguousarray(field, np.float32)
+        out = np.empty((nyy, nxx), np.float32)
+        self._check(self._L.octane_zoom_in_float(self._h, _ptr(field), nx, ny, _ptr(out), nxx, nyy, interp))
+        return out
+
     def oct_uv2pix(self, nav: Nav, t1: float, t2: float, lat, lon, x, y, u, v, p: Optional[Params] = None) -> int:
         """u, v: first-guess winds (m/s) in, pixel displacements out (in place).  Returns 1 when the
         sector-moved guard zeroed them."""

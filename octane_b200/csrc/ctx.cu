@@ -1033,6 +1033,34 @@ int octane_band_minmax(int band, float* maxch, float* minch)
     return OCTANE_OK;
 }
 
+int octane_zoom_in_float_dev(octane_ctx* c, const float* d_in, int nx, int ny, float* d_out, int nxx, int nyy, int interp)
+{
+    if (!c || !d_in || !d_out || nx <= 0 || ny <= 0 || nxx < nx || nyy < ny) { set_err("null or invalid argument"); return OCTANE_EINVAL; }
+    CUDA_OK(cudaSetDevice(c->device));
+    launch_zoom_in_float(d_in, nx, ny, d_out, nxx, nyy, interp, c->stream);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return OCTANE_OK;
+}
+
+int octane_zoom_in_float(octane_ctx* c, const float* in, int nx, int ny, float* out, int nxx, int nyy, int interp)
+{
+    if (!c || !in || !out || nx <= 0 || ny <= 0 || nxx < nx || nyy < ny) { set_err("null or invalid argument"); return OCTANE_EINVAL; }
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t ib = align_up((size_t)nx * ny * sizeof(float)), ob = (size_t)nxx * nyy * sizeof(float);
+    int rc = ensure_stage(c, ib + ob);
+    if (rc) return rc;
+    float* d_in = (float*)c->stage;
+    float* d_out = (float*)(c->stage + ib);
+    begin_call(c);
+    CUDA_OK(cudaMemcpyAsync(d_in, in, (size_t)nx * ny * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    rc = octane_zoom_in_float_dev(c, d_in, nx, ny, d_out, nxx, nyy, interp);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return OCTANE_OK;
+}
+
 int octane_uv2pix_dev(octane_ctx* c, const octane_nav* nav, double t1, double t2, const float* d_lat,
                       const float* d_lon, const short* d_x, const short* d_y, int nx, int ny,
                       const octane_params* p, float* d_u, float* d_v)

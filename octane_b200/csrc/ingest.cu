@@ -130,4 +130,56 @@ void launch_uv2pix(float* u, float* v, const float* lat, const float* lon, const
     k_uv2pix<<<grid, 256, 0, st>>>(u, v, lat, lon, xs, ys, nx, ny, q);
 }
 
+
+// ---- regridding of an ancillary field onto the image grid: oct_zoom_in_float, src/oct_zoom.cc:180-222,
+// with oct_bicubic_float / oct_cell, src/oct_bicubic.cc:12-29,100-150 (bicubic when interp == 1, nearest
+// neighbour otherwise).  The reader uses it for cloud-top heights and extra channels that come on a
+// coarser grid than channel 1 (src/oct_fileread.cc:370,796).  One thread per output pixel; the 16 taps
+// of a 4x upsampling hit the same cache lines for neighbouring threads, so the pass is bound by the 4 B
+// written per pixel.
+__device__ __forceinline__ double zcell(double v0, double v1, double v2, double v3, double x)
+{
+    return v1 + 0.5 * x * (v2 - v0 + x * (2.0 * v0 - 5.0 * v1 + 4.0 * v2 - v3 + x * (3.0 * (v1 - v2) + v3 - v0)));
+}
+__device__ __forceinline__ int zbc(int x, int n) { return x < 0 ? 0 : (x >= n ? n - 1 : x); }
+
+__global__ void __launch_bounds__(256)
+k_zoom_in_float(const float* __restrict__ in, int nx, int ny, float* __restrict__ out, int nxx, int nyy, int interp)
+{
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int jj1 = blockIdx.y;
+    if (i1 >= nxx || jj1 >= nyy) return;
+    const float factorx = ((float)nxx / nx);
+    const float factory = ((float)nyy / ny);
+    const float val1 = (0.5 - 0.5 / factory);
+    const float val2 = (0.5 - 0.5 / factorx);
+    const float j2 = (float)((jj1 / factory) - val1);
+    const float i2 = (float)((i1 / factorx) - val2);
+    float g;
+    if (interp == 1) {
+        const double uu = i2, vv = j2;
+        const int x = zbc((int)uu, nx), y = zbc((int)vv, ny);
+        const int mx = zbc((int)(uu - 1), nx), my = zbc((int)(vv - 1), ny);
+        const int dx = zbc((int)(uu + 1), nx), dy = zbc((int)(vv + 1), ny);
+        const int ddx = zbc((int)(uu + 2), nx), ddy = zbc((int)(vv + 2), ny);
+        const int cols[4] = { mx, x, dx, ddx };
+        const size_t rows[4] = { (size_t)nx * my, (size_t)nx * y, (size_t)nx * dy, (size_t)nx * ddy };
+        double v[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)          // pol[c][r] = input[cols[c] + rows[r]]; first along y, then along x
+            v[c] = zcell(in[cols[c] + rows[0]], in[cols[c] + rows[1]], in[cols[c] + rows[2]], in[cols[c] + rows[3]], vv - y);
+        g = zcell(v[0], v[1], v[2], v[3], uu - x);
+    } else {
+        const int j3 = int(j2 + 0.5), i3 = int(i2 + 0.5);
+        g = in[i3 + (size_t)nx * j3];
+    }
+    out[i1 + (size_t)nxx * jj1] = g;
+}
+
+void launch_zoom_in_float(const float* in, int nx, int ny, float* out, int nxx, int nyy, int interp, cudaStream_t st)
+{
+    dim3 grid((nxx + 255) / 256, nyy);
+    k_zoom_in_float<<<grid, 256, 0, st>>>(in, nx, ny, out, nxx, nyy, interp);
+}
+
 }  // namespace octane

@@ -109,6 +109,7 @@ struct Uv2PixParams {
     double secs, req, req2, rpol, rpol2, eval, lam0, pph;
     float xscale, xoffset, yscale, yoffset;
 };
+void launch_zoom_in_float(const float* in, int nx, int ny, float* out, int nxx, int nyy, int interp, cudaStream_t st);
 void launch_uv2pix(float* u, float* v, const float* lat, const float* lon, const short* xs, const short* ys, int nx,
                    int ny, const Uv2PixParams& q, cudaStream_t st);
 

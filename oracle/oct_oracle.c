@@ -789,3 +789,43 @@ int oracle_uv2pix(const oracle_nav *nav, double t1, double t2,
         }
     return 0;
 }
+
+/* ---- regridding: oct_zoom_in_float, src/oct_zoom.cc:180-222 + oct_bicubic_float / oct_cell,
+ * src/oct_bicubic.cc:12-29,100-150 */
+static double zcell(const double v[4], double x)
+{
+    return v[1] + 0.5 * x * (v[2] - v[0] + x * (2.0 * v[0] - 5.0 * v[1] + 4.0 * v[2] - v[3] + x * (3.0 * (v[1] - v[2]) + v[3] - v[0])));
+}
+static int zbc(int x, int n) { return x < 0 ? 0 : (x >= n ? n - 1 : x); }
+
+int oracle_zoom_in_float(const float *in, int nx, int ny, float *out, int nxx, int nyy, int interp)
+{
+    const float factorx = ((float)nxx / nx), factory = ((float)nyy / ny);
+    const float val1 = (0.5 - 0.5 / factory), val2 = (0.5 - 0.5 / factorx);
+#pragma omp parallel for schedule(static)
+    for (int jj1 = 0; jj1 < nyy; jj1++) {
+        const float j2 = (float)((jj1 / factory) - val1);
+        for (int i1 = 0; i1 < nxx; i1++) {
+            const float i2 = (float)((i1 / factorx) - val2);
+            float g;
+            if (interp == 1) {
+                const double uu = i2, vv = j2;
+                const int x = zbc((int)uu, nx), y = zbc((int)vv, ny);
+                const int cols[4] = { zbc((int)(uu - 1), nx), x, zbc((int)(uu + 1), nx), zbc((int)(uu + 2), nx) };
+                const int rows[4] = { zbc((int)(vv - 1), ny), y, zbc((int)(vv + 1), ny), zbc((int)(vv + 2), ny) };
+                double v[4];
+                for (int c = 0; c < 4; c++) {
+                    double p[4];
+                    for (int r = 0; r < 4; r++) p[r] = in[cols[c] + (size_t)nx * rows[r]];
+                    v[c] = zcell(p, vv - y);
+                }
+                g = zcell(v, uu - x);
+            } else {
+                const int j3 = (int)(j2 + 0.5), i3 = (int)(i2 + 0.5);
+                g = in[i3 + (size_t)nx * j3];
+            }
+            out[i1 + (size_t)nxx * jj1] = g;
+        }
+    }
+    return 0;
+}

@@ -184,6 +184,27 @@ def uv2pix(nav, t1, t2, lat, lon, x, y, u, v):
     return u, v, rc
 
 
+def zoom_in_float(field, nxx, nyy, interp=1):
+    field = np.ascontiguousarray(field, np.float32)
+    ny, nx = field.shape
+    L = lib()
+    L.oracle_zoom_in_float.argtypes = [_f32, C.c_int, C.c_int, _f32, C.c_int, C.c_int, C.c_int]
+    out = np.zeros((nyy, nxx), np.float32)
+    L.oracle_zoom_in_float(field, nx, ny, out, nxx, nyy, interp)
+    return out
+
+
+def ref_zoom_in_float(field, nxx, nyy, interp=1):
+    """the reference's own CPU function (oracle/_ref/libref_cpu.so; no GPU needed)"""
+    field = np.ascontiguousarray(field, np.float32)
+    ny, nx = field.shape
+    L = ref_cpu()
+    L.ref_zoom_in_float.argtypes = [_f32, _f32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    out = np.zeros((nyy, nxx), np.float32)
+    L.ref_zoom_in_float(field, out, nx, ny, nxx, nyy, interp)
+    return out
+
+
 # ---- the reference itself -------------------------------------------------
 _ref_cpu = None
 _ref_cuda = None

@@ -24,6 +24,7 @@
 void oct_patch_match_optical_flow(float*, float*, float*, float*, int, int, OFFlags);
 void oct_zoom_out(double*, double*, int, int, double, int);
 void oct_zoom_in(double*, double*, int, int, int, int);
+void oct_zoom_in_float(float*, float*, int, int, int, int, int, int);
 #ifdef REF_WITH_CUDA
 void oct_variational_optical_flow(Image, Image, float*, float*, float*, int, int, int, OFFlags);
 void oct_pix2uv_cuda(GOESVar&, double, float*, float*, short*, short*, short*, short*, OFFlags);
@@ -87,6 +88,12 @@ int ref_patch_match(const float* g1, const float* g2, float* u, float* v, int nx
 int ref_zoom_out(const double* in, double* out, int nx, int ny, double factor)
 {
     oct_zoom_out(const_cast<double*>(in), out, nx, ny, factor, 0);
+    return 0;
+}
+
+int ref_zoom_in_float(const float* in, float* out, int nx, int ny, int nxx, int nyy, int interp)
+{
+    oct_zoom_in_float(const_cast<float*>(in), out, nx, ny, nxx, nyy, 0, interp);      // src/oct_zoom.cc:180
     return 0;
 }
 
