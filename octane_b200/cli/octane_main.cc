@@ -11,9 +11,10 @@
 // Differences from the reference, all forced by this image having no netcdf-cxx4 / HDF5:
 //   * files are classic NetCDF (CDF-1 / CDF-2), read and written by csrc/cdf.cc; the schema
 //     (dimension / variable / attribute names, types, order) is the reference's;
-//   * -Polar / -Merc readers, -sosm, -srsal, -interp and regridding of a second channel or a
-//     cloud-top-height field that lives on another grid are not built (off the
-//     variational GOES path); the program says so and stops instead of silently doing less.
+//   * -Polar / -Merc readers, -sosm, -srsal, -interp and the DOWN-scaling of an extra channel or a
+//     cloud-top-height field that is finer than channel 1 (oct_zoom_out_float) are not built (SURVEY.md
+//     section 2: off the variational GOES path); the program says so and stops instead of silently doing
+//     less.  Coarser fields are brought up with octane_zoom_in_float (oct_zoom_in_float).
 // Quirks kept: -cgiters is documented but never parsed (:144); -corn leaves docorn = 0 (:270-273);
 // -scsig stores the square (:229); -set_device is 1-based (:313); -normmax/-normmin only change
 // the attribute written, the normalisation always uses the band table (oct_fileread.cc:344-388).
@@ -132,7 +133,8 @@ bool read_goes(const std::string& path, Scene& s, std::string* err)
     return true;
 }
 
-bool read_plane(const std::string& path, const char* var, int nx, int ny, std::vector<float>& out, std::string* err)
+// a float field with dimensions (ny, nx) as the CLAVR-x / first-guess readers expect (oct_fileread.cc:754-859)
+bool read_plane(const std::string& path, const char* var, int* fx_out, int* fy_out, std::vector<float>& out, std::string* err)
 {
     cdf::Reader f;
     if (f.open(path)) { *err = f.error(); return false; }
@@ -140,22 +142,40 @@ bool read_plane(const std::string& path, const char* var, int nx, int ny, std::v
     if (f.dim_len("nx", &fx) || f.dim_len("ny", &fy)) { *err = path + ": no nx / ny dimension"; return false; }
     const cdf::Var* v = f.var(var);
     if (!v || v->nelems != fx * fy) { *err = path + ": " + var + " missing or misshapen"; return false; }
-    if ((int)fx != nx || (int)fy != ny) {
-        *err = path + ": field is " + std::to_string(fx) + "x" + std::to_string(fy) + ", image is " + std::to_string(nx) + "x" +
-               std::to_string(ny) + "; regridding (oct_zoom_in_float / oct_zoom_out_float) is not built";
+    out.resize((size_t)fx * fy);
+    if (f.get_float(v, out.data())) { *err = f.error(); return false; }
+    *fx_out = (int)fx; *fy_out = (int)fy;
+    return true;
+}
+
+// Bring a field of size fx*fy onto the nx*ny image grid the way the readers do (oct_fileread.cc:361-380,
+// 794-806): same size -> unchanged (oct_zoom_out_float with factor 1 copies, oct_zoom.cc:79-86); coarser ->
+// oct_zoom_in_float (bicubic, or nearest neighbour with -nncth); finer -> oct_zoom_out_float, not built.
+// ctx == nullptr (dry run): only the same-size case.
+bool regrid(octane_ctx* ctx, const std::string& what, std::vector<float>& field, int fx, int fy, int nx, int ny, int interp,
+            std::string* err)
+{
+    if (fx == nx && fy == ny) return true;
+    if (fx > nx || fy > ny || !ctx) {
+        *err = what + " is " + std::to_string(fx) + "x" + std::to_string(fy) + ", image is " + std::to_string(nx) + "x" +
+               std::to_string(ny) + (ctx ? "; down-scaling a finer field (oct_zoom_out_float) is not built"
+                                         : "; regridding needs the GPU (not available in a dry run)");
         return false;
     }
-    out.resize((size_t)nx * ny);
-    if (f.get_float(v, out.data())) { *err = f.error(); return false; }
+    std::vector<float> out((size_t)nx * ny);
+    if (octane_zoom_in_float(ctx, field.data(), fx, fy, out.data(), nx, ny, interp) < 0) { *err = octane_last_error(); return false; }
+    field.swap(out);
     return true;
 }
 
 // ---- writer: oct_goeswrite, src/oct_filewrite.cc:17-349 ----------------------------------------
 bool write_goes(const std::string& path, const Scene& s, const Flags& a, const octane_nav& nav, float dT,
                 const short* U, const short* V, const short* Ur, const short* Vr, const float* upix, const float* vpix,
-                const short* ctp, std::string* err)
+                const short* ctp, std::string* err, const Scene* const* extra = nullptr)
 {
     using cdf::Att;
+    const Scene* e2 = extra ? extra[0] : nullptr;      // channel 2 / 3 of image 1, when on the same grid
+    const Scene* e3 = extra ? extra[1] : nullptr;
     cdf::Writer w;
     if (w.create(path)) { *err = w.error(); return false; }
     const int xd = w.add_dim("x", s.nx), yd = w.add_dim("y", s.ny);
@@ -174,13 +194,22 @@ bool write_goes(const std::string& path, const Scene& s, const Flags& a, const o
     if (a.outraw) { urV = w.add_var("U_raw", cdf::SHORT, yx); vrV = w.add_var("V_raw", cdf::SHORT, yx); }
     if (a.pixuv == 1) { upV = w.add_var("Upix", cdf::FLOAT, yx); vpV = w.add_var("Vpix", cdf::FLOAT, yx); }
     if (a.outctp && a.doCTH == 1) ctpV = w.add_var("CTP", cdf::SHORT, yx);
-    if (a.outrad) radV = w.add_var("Rad", cdf::SHORT, yx);
+    int rad2V = -1, rad3V = -1;
+    if (a.outrad) {
+        radV = w.add_var("Rad", cdf::SHORT, yx);
+        if (e2) rad2V = w.add_var("Rad2", cdf::SHORT, yx);
+        if (e3) rad3V = w.add_var("Rad3", cdf::SHORT, yx);
+    }
     const int gipV = w.add_var("goes_imager_projection", cdf::INT, {});
     const int ofV = w.add_var("optical_flow_settings", cdf::INT, {});
-    int pk[5] = { -1, -1, -1, -1, -1 };
+    int pk[3][5];
+    for (int c = 0; c < 3; c++) for (int k = 0; k < 5; k++) pk[c][k] = -1;
     if (a.outrad) {
         const char* names[5] = { "planck_fk1", "planck_fk2", "planck_bc1", "planck_bc2", "kappa0" };
-        for (int k = 0; k < 5; k++) pk[k] = w.add_var(names[k], cdf::FLOAT, {});
+        const char* suffix[3] = { "", "_2", "_3" };
+        const bool have[3] = { true, e2 != nullptr, e3 != nullptr };
+        for (int c = 0; c < 3; c++)
+            if (have[c]) for (int k = 0; k < 5; k++) pk[c][k] = w.add_var(std::string(names[k]) + suffix[c], cdf::FLOAT, {});
     }
     const char* gm = "goes_imager_projection";
     if (a.outnav) {
@@ -204,6 +233,14 @@ bool write_goes(const std::string& path, const Scene& s, const Flags& a, const o
     if (a.outrad) {
         w.put_att(radV, Att::text("long_name", "Rad")); w.put_att(radV, Att::text("grid_mapping", gm));
         w.put_att(radV, Att::f32("scale_factor", s.radScale)); w.put_att(radV, Att::f32("add_offset", s.radOffset));
+        const Scene* es[2] = { e2, e3 };
+        const int ev[2] = { rad2V, rad3V };
+        for (int c = 0; c < 2; c++) {
+            if (!es[c]) continue;
+            w.put_att(ev[c], Att::text("long_name", "Rad2"));          // sic: both extra channels, oct_filewrite.cc:195,202
+            w.put_att(ev[c], Att::text("grid_mapping", gm));
+            w.put_att(ev[c], Att::f32("scale_factor", es[c]->radScale)); w.put_att(ev[c], Att::f32("add_offset", es[c]->radOffset));
+        }
     }
     w.put_att(gipV, Att::text("long_name", "GOES-R ABI fixed grid projection"));
     w.put_att(gipV, Att::text("grid_mapping_name", "geostationary"));
@@ -241,13 +278,21 @@ bool write_goes(const std::string& path, const Scene& s, const Flags& a, const o
     if (a.outraw) { rc |= w.put_var(urV, Ur, n); rc |= w.put_var(vrV, Vr, n); }
     if (a.pixuv == 1) { rc |= w.put_var(upV, upix, n); rc |= w.put_var(vpV, vpix, n); }
     if (ctpV >= 0) rc |= w.put_var(ctpV, ctp, n);
-    if (a.outrad) rc |= w.put_var(radV, s.rad.data(), n);
+    if (a.outrad) {
+        rc |= w.put_var(radV, s.rad.data(), n);
+        if (e2) rc |= w.put_var(rad2V, e2->rad.data(), n);
+        if (e3) rc |= w.put_var(rad3V, e3->rad.data(), n);
+    }
     const int gv = (int)s.gipVal, ofv = a.oftype;
     rc |= w.put_var(gipV, &gv, 1);
     rc |= w.put_var(ofV, &ofv, 1);
     if (a.outrad) {
-        const float pv[5] = { s.fk1, s.fk2, s.bc1, s.bc2, s.kap1 };
-        for (int k = 0; k < 5; k++) rc |= w.put_var(pk[k], &pv[k], 1);
+        const Scene* sc[3] = { &s, e2, e3 };
+        for (int c = 0; c < 3; c++) {
+            if (!sc[c]) continue;
+            const float pv[5] = { sc[c]->fk1, sc[c]->fk2, sc[c]->bc1, sc[c]->bc2, sc[c]->kap1 };
+            for (int k = 0; k < 5; k++) rc |= w.put_var(pk[c][k], &pv[k], 1);
+        }
     }
     if (rc || w.close()) { *err = w.error(); return false; }
     return true;
@@ -345,7 +390,10 @@ int main(int argc, char* argv[])
     }
     if (args.dopolar || args.domerc) return fail("-Polar / -Merc readers are not part of this build (GOES fixed-grid path only)");
     if (args.dososm) return fail("-sosm (CPU patch-match solver) is not part of this build");
-    if (args.doc2 || args.doc3) return fail("-ic21/-ic31 extra channels are not wired into this program yet (the solver itself takes nc <= 3)");
+    if ((args.doc2 && fc22 == "none") || (args.doc3 && fc32 == "none")) {       // src/main.cc:352-361
+        printf("Missing files for second / third channel...stopping \n");
+        return 0;
+    }
     if (args.dosrsal) printf("Warning: -srsal smoothing is not part of this build; output is unsmoothed\n");
     if (args.dointerp) printf("Warning: -interp is not part of this build; only outfile.nc is written\n");
 
@@ -366,7 +414,10 @@ int main(int argc, char* argv[])
         if (octane_band_minmax(g1.band, &args.NormMax, &args.NormMin)) return fail("band_id outside 1..16");
         std::vector<short> z(n, 0);
         std::vector<float> zf(n, 0.f), cth0;
-        if (args.doCTH == 1 && !read_plane(f1c, "Cloud_Top_Height_Effective", nx, ny, cth0, &err)) return fail(err);
+        int cx = 0, cy = 0;
+        if (args.doCTH == 1 && (!read_plane(f1c, "Cloud_Top_Height_Effective", &cx, &cy, cth0, &err) ||
+                                !regrid(nullptr, "cloud-top height field", cth0, cx, cy, nx, ny, args.interpcth, &err)))
+            return fail(err);
         for (size_t k = 0; k < cth0.size(); k++) z[k] = args.ir == 1 ? (short)((cth0[k] - 300) * 100) : (short)cth0[k];
         std::vector<short> zero(n, 0);
         const std::string outname0 = outdir + "outfile.nc";
@@ -389,26 +440,50 @@ int main(int argc, char* argv[])
     nav.g2xOffset = g2.xOffset; nav.g2yOffset = g2.yOffset;                                      // main.cc:401-405
     nav.minX = 0; nav.minY = 0;
 
-    // ingest both files (oct_fileread.cc:341-388): band table range, 0..255, cal "RAW"
-    Scene* both[2] = { &g1, &g2 };
-    for (int k = 0; k < 2; k++) {
-        Scene& s = *both[k];
+    // ingest (oct_fileread.cc:341-388): band table range, 0..255, cal "RAW"; navigation for image 1 only
+    auto ingest = [&](Scene& s, int donav, int channel) -> bool {
         octane_cal cal;
         memset(&cal, 0, sizeof cal);
         cal.radScale = s.radScale; cal.radOffset = s.radOffset;
         cal.fk1 = s.fk1; cal.fk2 = s.fk2; cal.bc1 = s.bc1; cal.bc2 = s.bc2; cal.kap1 = s.kap1;
-        if (octane_band_minmax(s.band, &cal.maxin, &cal.minin)) return fail("band_id outside 1..16");
-        cal.maxout = 255.f; cal.minout = 0.f; cal.H = s.pph + s.req; cal.cal = 0; cal.donav = (k == 0);
-        if (k == 0) {
+        if (octane_band_minmax(s.band, &cal.maxin, &cal.minin)) { err = "band_id outside 1..16"; return false; }
+        cal.maxout = 255.f; cal.minout = 0.f; cal.H = s.pph + s.req; cal.cal = 0; cal.donav = donav;
+        if (donav && channel == 1) {
             if (args.setNormMax) args.NormMax = cal.maxin;
             if (args.setNormMin) args.NormMin = cal.minin;
         }
         octane_nav ns = nav;
         ns.req = s.req; ns.rpol = s.rpol; ns.pph = s.pph; ns.lam0 = s.lam0;
         ns.xScale = s.xScale; ns.xOffset = s.xOffset; ns.yScale = s.yScale; ns.yOffset = s.yOffset;
-        s.data.resize(n); s.lat.resize(n); s.lon.resize(n);
-        if (octane_navcal(ctx, s.rad.data(), s.x.data(), s.y.data(), nx, ny, &ns, &cal, s.data.data(), s.lat.data(), s.lon.data()) < 0)
-            return fail(octane_last_error());
+        const size_t m = (size_t)s.nx * s.ny;
+        s.data.resize(m); s.lat.resize(m); s.lon.resize(m);
+        if (octane_navcal(ctx, s.rad.data(), s.x.data(), s.y.data(), s.nx, s.ny, &ns, &cal, s.data.data(), s.lat.data(),
+                          s.lon.data()) < 0) { err = octane_last_error(); return false; }
+        return true;
+    };
+    if (!ingest(g1, 1, 1) || !ingest(g2, 0, 1)) return fail(err);
+
+    // extra channels (-ic21/-ic22, -ic31/-ic32; main.cc:414-436, oct_fileread.cc:359-380): channel planes
+    // behind channel 1, each brought to channel 1's grid
+    const int nc = 1 + args.doc2 + args.doc3;
+    std::vector<float> img1(g1.data), img2(g2.data);
+    Scene extra[2][2];                     // [channel 2 / 3][image 1 / 2]
+    bool extra_same_grid[2] = { false, false };
+    {
+        const std::string* files[2][2] = { { &fc21, &fc22 }, { &fc31, &fc32 } };
+        const int on[2] = { args.doc2, args.doc3 };
+        for (int ch = 0; ch < 2; ch++) {
+            if (!on[ch]) continue;
+            for (int im = 0; im < 2; im++) {
+                Scene& e = extra[ch][im];
+                if (!read_goes(*files[ch][im], e, &err) || !ingest(e, im == 0, ch + 2)) return fail(err);
+                std::vector<float> plane(e.data);
+                if (!regrid(ctx, "channel " + std::to_string(ch + 2), plane, e.nx, e.ny, nx, ny, 1, &err)) return fail(err);
+                std::vector<float>& dst = im == 0 ? img1 : img2;
+                dst.insert(dst.end(), plane.begin(), plane.end());
+            }
+            extra_same_grid[ch] = extra[ch][0].nx == nx && extra[ch][0].ny == ny;
+        }
     }
 
     octane_params p;
@@ -419,10 +494,15 @@ int main(int argc, char* argv[])
     p.first_guess = args.dofirstguess;
 
     std::vector<float> cth, upix(n, 0.f), vpix(n, 0.f);
-    if (args.doCTH == 1 && !read_plane(f1c, "Cloud_Top_Height_Effective", nx, ny, cth, &err)) return fail(err);
+    int cx = 0, cy = 0;
+    if (args.doCTH == 1 && (!read_plane(f1c, "Cloud_Top_Height_Effective", &cx, &cy, cth, &err) ||
+                            !regrid(ctx, "cloud-top height field", cth, cx, cy, nx, ny, args.interpcth, &err)))
+        return fail(err);
     if (args.dofirstguess == 1) {
         // oct_fgread (oct_fileread.cc:817-859) + oct_uv2pix (oct_optical_flow.cc:51-53)
-        if (!read_plane(f1fg, "UFG", nx, ny, upix, &err) || !read_plane(f1fg, "VFG", nx, ny, vpix, &err)) return fail(err);
+        int ux = 0, uy = 0, vx = 0, vy = 0;
+        if (!read_plane(f1fg, "UFG", &ux, &uy, upix, &err) || !read_plane(f1fg, "VFG", &vx, &vy, vpix, &err)) return fail(err);
+        if (ux != nx || uy != ny || vx != nx || vy != ny) return fail("first-guess file must have the image's dimensions (offlags.h:13)");
         if (octane_uv2pix(ctx, &nav, g1.t, g2.t, g1.lat.data(), g1.lon.data(), g1.x.data(), g1.y.data(), nx, ny, &p,
                           upix.data(), vpix.data()) < 0)
             return fail(octane_last_error());
@@ -430,7 +510,7 @@ int main(int argc, char* argv[])
 
     std::vector<short> U(n), V(n), Ur(n), Vr(n), ctp(args.doCTH == 1 ? n : 0);
     float dT = 0.f;
-    rc = octane_optical_flow(ctx, g1.data.data(), g2.data.data(), args.doCTH == 1 ? cth.data() : nullptr, nx, ny, 1, &nav,
+    rc = octane_optical_flow(ctx, img1.data(), img2.data(), args.doCTH == 1 ? cth.data() : nullptr, nx, ny, nc, &nav,
                              g1.t, g2.t, &p, upix.data(), vpix.data(), U.data(), V.data(), Ur.data(), Vr.data(),
                              args.doCTH == 1 ? ctp.data() : nullptr, &dT);
     if (rc < 0) return fail(octane_last_error());
@@ -438,8 +518,12 @@ int main(int argc, char* argv[])
         printf("MOVE WARNING: Sector Moved, setting motions to 0 %g %g %g %g\n", nav.xOffset, nav.g2xOffset, nav.yOffset, nav.g2yOffset);
 
     const std::string outname = outdir + "outfile.nc";
+    const Scene* ex[2] = { (args.doc2 && extra_same_grid[0]) ? &extra[0][0] : nullptr,
+                           (args.doc3 && extra_same_grid[1]) ? &extra[1][0] : nullptr };
+    if ((args.doc2 && !ex[0]) || (args.doc3 && !ex[1]))
+        printf("Warning: Rad2/Rad3 are written only for channels on channel 1's grid\n");
     if (!write_goes(outname, g1, args, nav, dT, U.data(), V.data(), Ur.data(), Vr.data(), upix.data(), vpix.data(),
-                    args.doCTH == 1 ? ctp.data() : nullptr, &err))
+                    args.doCTH == 1 ? ctp.data() : nullptr, &err, ex))
         return fail(err);
     printf("%s written\n", outname.c_str());
     octane_ctx_destroy(ctx);

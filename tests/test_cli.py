@@ -57,14 +57,14 @@ def test_flags_and_reference_quirks():
     assert "Farneback disabled" in r.stdout
 
 
-def _pair_files(tmp, nx=96, ny=80, band=2, cth=False, sector="meso_0.5km"):
+def _pair_files(tmp, nx=96, ny=80, band=2, cth=False, sector="meso_0.5km", seed=21, prefix=""):
     c = dict(sector=sector, nx=nx, ny=ny, x0=10, y0=20)
     xs, ys, xo, yo, dt = S.SECTORS[sector]
-    i1, i2, _, _ = S.make_pair(nx, ny, 21)
+    i1, i2, _, _ = S.make_pair(nx, ny, seed)
     maxin, minin = ob.band_minmax(band)
     radScale, radOffset = (maxin - minin) / 4000.0, minin
     xc = (np.arange(nx) + c["x0"]).astype(np.int16); yc = (np.arange(ny) + c["y0"]).astype(np.int16)
-    f1, f2 = os.path.join(tmp, "g1.nc"), os.path.join(tmp, "g2.nc")
+    f1, f2 = os.path.join(tmp, prefix + "g1.nc"), os.path.join(tmp, prefix + "g2.nc")
     r1 = G.counts_from_image(i1, maxin, minin, radScale, radOffset); r2 = G.counts_from_image(i2, maxin, minin, radScale, radOffset)
     G.write_goes_l1b(f1, r1, xc, yc, 1000.0, band, xs, xo, ys, yo, radScale, radOffset)
     G.write_goes_l1b(f2, r2, xc, yc, 1000.0 + dt, band, xs, xo, ys, yo, radScale, radOffset)
@@ -129,7 +129,7 @@ def test_reader_rejects_what_it_cannot_read(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["default", "pd_cth", "firstguess"])
+@pytest.mark.parametrize("mode", ["default", "pd_cth", "firstguess", "cth_coarse_nn", "two_channels"])
 def test_cli_end_to_end_matches_the_library(tmp_path, ctx, mode):
     """file -> octane -> outfile.nc equals ingest + flow + navigation called through the C ABI"""
     from scipy.io import netcdf_file
@@ -153,6 +153,23 @@ def test_cli_end_to_end_matches_the_library(tmp_path, ctx, mode):
         G.write_plane_file(os.path.join(tmp, "cth.nc"), Cloud_Top_Height_Effective=cth)
         args += ["-pd", "-i1cth", os.path.join(tmp, "cth.nc"), "-alpha", "8", "-kiters", "3"]
         p = ob.default_params(pixuv=1, doCTH=1, alpha=8.0, kiters=3)
+    nc = 1
+    if mode == "cth_coarse_nn":       # CTH on a 4x coarser grid, nearest-neighbour remap (-nncth)
+        small = (6000 + 5000 * np.cos(np.arange(nx // 4)[None, :] / 5.0) * np.sin(np.arange(ny // 4)[:, None] / 7.0)).astype(np.float32)
+        G.write_plane_file(os.path.join(tmp, "cth4.nc"), Cloud_Top_Height_Effective=small)
+        args += ["-i1cth", os.path.join(tmp, "cth4.nc"), "-nncth", "-ir"]
+        p = ob.default_params(doCTH=1, ir=1)
+        cth = ctx.oct_zoom_in_float(small, nx, ny, 0)
+    if mode == "two_channels":        # -ic21 / -ic22: a second channel on the same grid
+        d2 = _pair_files(os.path.join(tmp), nx=160, ny=128, band=13, seed=33, prefix="c2_")
+        args += ["-ic21", d2["f1"], "-ic22", d2["f2"]]
+        cal2 = ob.goes_cal(d2["radScale"], d2["radOffset"], band=13, fk1=202263.0, fk2=3698.19, bc1=0.43361, bc2=0.99939,
+                           kap1=0.0019486)
+        a2, _, _ = ctx.oct_navcal_cuda(d2["r1"], d2["xc"], d2["yc"], nav, cal2)
+        cal2.donav = 0
+        b2, _, _ = ctx.oct_navcal_cuda(d2["r2"], d2["xc"], d2["yc"], nav, cal2)
+        img1 = np.ascontiguousarray(np.stack([img1, a2])); img2 = np.ascontiguousarray(np.stack([img2, b2]))
+        nc = 2
     if mode == "firstguess":
         ufg, vfg = cases.uv2pix_winds(nx, ny)
         G.write_plane_file(os.path.join(tmp, "fg.nc"), UFG=ufg, VFG=vfg)
@@ -161,7 +178,7 @@ def test_cli_end_to_end_matches_the_library(tmp_path, ctx, mode):
         u0, v0 = ufg.copy(), vfg.copy()
         ctx.oct_uv2pix(nav, 1000.0, 1000.0 + d["dt"], lat, lon, d["xc"], d["yc"], u0, v0, p)
     run(*args)
-    want = ctx.oct_optical_flow(img1, img2, nav, 1000.0, 1000.0 + d["dt"], p, cth=cth, upix=u0, vpix=v0)
+    want = ctx.oct_optical_flow(img1, img2, nav, 1000.0, 1000.0 + d["dt"], p, cth=cth, upix=u0, vpix=v0, nc=nc)
     f = netcdf_file(os.path.join(tmp, "outfile.nc"), "r", mmap=False)
     v = f.variables
     for name, key in (("U", "uVal"), ("V", "vVal"), ("U_raw", "uVal2"), ("V_raw", "vVal2")):
@@ -169,6 +186,10 @@ def test_cli_end_to_end_matches_the_library(tmp_path, ctx, mode):
     if mode == "pd_cth":
         assert np.array_equal(v["Upix"][:], want["uPix"]) and np.array_equal(v["Vpix"][:], want["vPix"])
         assert np.array_equal(v["CTP"][:], want["CTP"]) and int(v["optical_flow_settings"].K_Iterations) == 3
+    if mode == "cth_coarse_nn":
+        assert np.array_equal(v["CTP"][:], want["CTP"]) and float(v["CTP"].interpcth) == 0.0
+    if mode == "two_channels":
+        assert np.array_equal(v["Rad2"][:], d2["r1"]) and "planck_fk1_2" in v and "Rad3" not in v
     assert int(v["optical_flow_settings"].dofirstguess) == int(mode == "firstguess")
     assert np.abs(v["U_raw"][:].astype(int)).max() > 20        # a real flow field came out (>0.2 px)
     f.close()

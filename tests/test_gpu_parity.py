@@ -409,3 +409,26 @@ def test_reference_signatures_of_ingest_drop_in(oracle):
     gu = load_golden("uv2pix_limb")
     ok = ~np.isnan(gu["upix"])
     assert np.abs(u - gu["upix"])[ok].max(initial=0) <= 1e-4 and np.abs(v - gu["vpix"])[ok].max(initial=0) <= 1e-4
+
+
+@pytest.mark.parametrize("dims", [((50, 60), (200, 240)), ((37, 41), (111, 123)), ((64, 64), (64, 64)), ((30, 45), (75, 113))])
+@pytest.mark.parametrize("interp", [1, 0])
+def test_zoom_in_float_matches_oracle_and_reference(ctx, oracle, dims, interp):
+    """oct_zoom_in_float (reference src/oct_zoom.cc:180): the regridding of cloud-top heights / extra
+    channels.  Checked against the CPU restatement and against the reference's own CPU object."""
+    (ny, nx), (nyy, nxx) = dims
+    f = (np.random.default_rng(nx * 7 + ny).standard_normal((ny, nx)) * 1000 + 5000).astype(np.float32)
+    got = ctx.oct_zoom_in_float(f, nxx, nyy, interp)
+    want = oracle.zoom_in_float(f, nxx, nyy, interp)
+    if interp == 0:
+        assert np.array_equal(got, want)                       # nearest neighbour: index arithmetic only
+    else:
+        assert np.abs(got - want).max() <= 1e-3                # values ~5000: one float ulp (FMA contraction in double)
+    got_dev = ctx.oct_zoom_in_float(dev(f), nxx, nyy, interp)
+    ctx.synchronize()
+    assert np.array_equal(got_dev.cpu().numpy(), got)
+    try:
+        ref = oracle.ref_zoom_in_float(f, nxx, nyy, interp)
+    except OSError:
+        pytest.skip("oracle/_ref/libref_cpu.so not built")
+    assert np.abs(got - ref).max() <= (0 if interp == 0 else 1e-3)
