@@ -28,6 +28,11 @@
  *                              src/oct_navcal_cuda.cu:100 (called by oct_goesread, src/oct_fileread.cc:383)
  *   octane_uv2pix*             void oct_uv2pix(GOESVar&,float*u,float*v,double t2,OFFlags)
  *                              src/oct_pix2uv_cuda.cu:372 (first-guess winds -> pixel displacements)
+ *   octane_navcal_grid         void oct_polar_navcal_cuda(float*data2,short*,short*x,short*y,short*,short*,int nx,int ny,
+ *                              int,int,int,int,float*data3,float*lat,float*lon,float xScale,float xOffset,float yScale,
+ *                              float yOffset,float lon0,float lat1,float R,int donav,int chan,OFFlags)
+ *                              src/oct_polar_navcal_cuda.cu:69, and oct_merc_navcal_cuda(... float lon0,float R,int donav,
+ *                              OFFlags) src/oct_merc_navcal_cuda.cu:51 (ingest of the -Polar / -Merc grids)
  *   octane_band_minmax         void oct_bandminmax(int,float&,float&), src/oct_normalize_geo.cc:9
  *   octane_zoom_in_float       void oct_zoom_in_float(float*flow,float*flowout,int nx,int ny,int nxx,int nyy,
  *                              int cnum,int interp), src/oct_zoom.cc:180 (cloud-top heights / extra channels
@@ -171,6 +176,11 @@ int octane_optical_flow(octane_ctx* ctx, const float* img1, const float* img2, c
  * data/lat/lon: ny*nx floats out (lat and lon may both be NULL to skip navigation). */
 int octane_navcal(octane_ctx* ctx, const short* rad, const short* x, const short* y, int nx, int ny,
                   const octane_nav* nav, const octane_cal* cal, float* data, float* lat, float* lon);
+/* Ingest of the projected grids: grid 1 = orthographic polar (uses nav->lon0, nav->lat1, nav->R, degrees /
+ * metres as GOESNAVVar holds them), grid 2 = spherical Mercator (nav->lon1 in degrees, nav->R).  The float
+ * image passes through to data_out; lat/lon (degrees) may both be NULL. */
+int octane_navcal_grid(octane_ctx* ctx, int grid, const float* data, const short* x, const short* y, int nx, int ny,
+                       const octane_nav* nav, int donav, float* data_out, float* lat, float* lon);
 /* ABI band table: radiance range used for the normalisation; returns 0, or -2 for an unknown band
  * (the reference leaves maxch/minch uninitialised there). */
 int octane_band_minmax(int band, float* maxch, float* minch);
@@ -193,6 +203,13 @@ int octane_variational_flow_dev(octane_ctx* ctx, const float* d_img1, const floa
 int octane_pix2uv_dev(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
                       const float* d_u, const float* d_v, int nx, int ny, const octane_params* p,
                       short* d_U, short* d_V, short* d_U_raw, short* d_V_raw);
+/* The dispatcher on device buffers (solve + CTP pack + navigation, nothing copied, no host synchronisation):
+ * what a pipeline over many pairs calls, one context (= stream + workspace) per pair in flight.
+ * d_cth / d_ctp may be NULL when !p->doCTH. */
+int octane_optical_flow_dev(octane_ctx* ctx, const float* d_img1, const float* d_img2, const float* d_cth,
+                            int nx, int ny, int nc, const octane_nav* nav, double t1, double t2,
+                            const octane_params* p, float* d_upix_inout, float* d_vpix_inout,
+                            short* d_U, short* d_V, short* d_U_raw, short* d_V_raw, short* d_ctp);
 
 int octane_navcal_dev(octane_ctx* ctx, const short* d_rad, const short* d_x, const short* d_y, int nx, int ny,
                       const octane_nav* nav, const octane_cal* cal, float* d_data, float* d_lat, float* d_lon);

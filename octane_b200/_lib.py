@@ -60,9 +60,9 @@ EXPORTS = [
     "octane_ctx_create", "octane_ctx_destroy", "octane_ctx_set_profile", "octane_ctx_set_graphs",
     "octane_get_stats", "octane_ctx_synchronize", "octane_ctx_stream", "octane_workspace_bytes", "octane_level_dims",
     "octane_variational_flow", "octane_pix2uv", "octane_optical_flow",
-    "octane_variational_flow_dev", "octane_pix2uv_dev",
+    "octane_variational_flow_dev", "octane_pix2uv_dev", "octane_optical_flow_dev",
     "octane_navcal", "octane_navcal_dev", "octane_band_minmax", "octane_uv2pix", "octane_uv2pix_dev",
-    "octane_zoom_in_float", "octane_zoom_in_float_dev",
+    "octane_zoom_in_float", "octane_zoom_in_float_dev", "octane_navcal_grid",
     "octane_stage_blur_decimate", "octane_stage_gradient", "octane_stage_zoom_in",
     "octane_stage_build", "octane_stage_pcg",
     "octane_band_plan", "octane_comm_unique_id", "octane_comm_init", "octane_comm_rank",
@@ -105,12 +105,14 @@ def load() -> C.CDLL:
     L.octane_optical_flow.argtypes = [vp, vp, vp, vp, i, i, i, NP, d, d, PP, vp, vp, vp, vp, vp, vp, vp, fp]
     L.octane_variational_flow_dev.argtypes = [vp, vp, vp, i, i, i, PP, vp, vp]
     L.octane_pix2uv_dev.argtypes = [vp, NP, d, d, vp, vp, i, i, PP, vp, vp, vp, vp]
+    L.octane_optical_flow_dev.argtypes = [vp, vp, vp, vp, i, i, i, NP, d, d, PP, vp, vp, vp, vp, vp, vp, vp]
     CP = C.POINTER(Cal)
     L.octane_navcal.argtypes = [vp, vp, vp, vp, i, i, NP, CP, vp, vp, vp]
     L.octane_navcal_dev.argtypes = [vp, vp, vp, vp, i, i, NP, CP, vp, vp, vp]
     L.octane_band_minmax.argtypes = [i, fp, fp]
     L.octane_uv2pix.argtypes = [vp, NP, d, d, vp, vp, vp, vp, i, i, PP, vp, vp]
     L.octane_uv2pix_dev.argtypes = [vp, NP, d, d, vp, vp, vp, vp, i, i, PP, vp, vp]
+    L.octane_navcal_grid.argtypes = [vp, i, vp, vp, vp, i, i, NP, i, vp, vp, vp]
     L.octane_zoom_in_float.argtypes = [vp, vp, i, i, vp, i, i, i]
     L.octane_zoom_in_float_dev.argtypes = [vp, vp, i, i, vp, i, i, i]
     L.octane_stage_blur_decimate.argtypes = [vp, vp, i, i, i, f, vp]

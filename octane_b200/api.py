@@ -254,6 +254,21 @@ class Context:
         out.update(uPix=upix, vPix=vpix, CTP=ctp, dT=dT.value)
         return out
 
+    def oct_optical_flow_dev(self, geo1, geo2, nav: Nav, t1: float, t2: float, p: Params, upix, vpix, ur, vr, ur2, vr2,
+                             cth=None, ctp=None, nc: int = 1, sync_torch: bool = True) -> int:
+        """Dispatcher on torch CUDA tensors, stream-ordered on the context's stream, no host synchronisation.
+        sync_torch=False skips the ordering against torch's current stream (the caller keeps several contexts
+        in flight and orders them itself: batch mode)."""
+        ny, nx = geo1.shape[-2:]
+        if sync_torch:
+            self._after_torch()
+        rc = self._check(self._L.octane_optical_flow_dev(self._h, _ptr(geo1), _ptr(geo2), _ptr(cth), nx, ny, nc, C.byref(nav),
+                                                         t1, t2, C.byref(p), _ptr(upix), _ptr(vpix), _ptr(ur), _ptr(vr),
+                                                         _ptr(ur2), _ptr(vr2), _ptr(ctp)))
+        if sync_torch:
+            self._before_torch()
+        return rc
+
     # ---- stage entry points (device pointers; parity tests)
     def stage_blur_decimate(self, d_img, nx, ny, nc, factor, d_out):
         self._after_torch()
@@ -289,6 +304,16 @@ class Context:
         self._check(self._L.octane_navcal(self._h, _ptr(rad), _ptr(x), _ptr(y), nx, ny, C.byref(nav), C.byref(cal),
                                           _ptr(data), _ptr(lat), _ptr(lon)))
         return data, lat, lon
+
+    def oct_navcal_grid(self, grid: int, data, x, y, nav: Nav, donav: int = 1):
+        """ingest of a -Polar (grid 1) / -Merc (grid 2) file: oct_polar_navcal_cuda / oct_merc_navcal_cuda.
+        Returns (data, lat, lon)."""
+        data = np.ascontiguousarray(data, np.float32); x = np.ascontiguousarray(x, np.int16); y = np.ascontiguousarray(y, np.int16)
+        ny, nx = data.shape
+        out = np.empty((ny, nx), np.float32); lat = np.empty((ny, nx), np.float32); lon = np.empty((ny, nx), np.float32)
+        self._check(self._L.octane_navcal_grid(self._h, grid, _ptr(data), _ptr(x), _ptr(y), nx, ny, C.byref(nav), donav,
+                                               _ptr(out), _ptr(lat), _ptr(lon)))
+        return out, lat, lon
 
     def oct_zoom_in_float(self, field, nxx: int, nyy: int, interp: int = 1):
         """regrid a coarser field onto an nyy x nxx grid (oct_zoom_in_float, src/oct_zoom.cc:180)"""

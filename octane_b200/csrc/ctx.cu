@@ -159,6 +159,8 @@ struct octane_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host-buffer entry points: result copies that overlap the next stage
+    cudaEvent_t ev_stage = nullptr;
     bool profile = false, graphs = true;
     bool use_tma = getenv("OCTANE_NO_TMA") == nullptr;   // developer switch: v1 pass-1 kernel everywhere
     Comm comm;
@@ -749,6 +751,13 @@ int octane_ctx_create(octane_ctx** out, int device)
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_err("cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return OCTANE_ECUDA; }
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
+        set_err("cudaStreamCreate (copy stream)");
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return OCTANE_ECUDA;
+    }
     memset(&c->stats, 0, sizeof c->stats);
     *out = c;
     return OCTANE_OK;
@@ -772,6 +781,8 @@ void octane_ctx_destroy(octane_ctx* c)
     if (c->d_gk) cudaFree(c->d_gk);
     if (c->h_its) cudaFreeHost(c->h_its);
     if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_stage) cudaEventDestroy(c->ev_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -879,6 +890,23 @@ int octane_pix2uv_band_dev(octane_ctx* c, const octane_nav* nav, double t1, doub
     return pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, row0, nrows, p, U, V, Ur, Vr);
 }
 
+int octane_optical_flow_dev(octane_ctx* c, const float* d_img1, const float* d_img2, const float* d_cth, int nx, int ny, int nc,
+                            const octane_nav* nav, double t1, double t2, const octane_params* p, float* d_u, float* d_v,
+                            short* U, short* V, short* Ur, short* Vr, short* d_ctp)
+{
+    if (!c || !d_img1 || !d_img2 || !nav || !p || !d_u || !d_v || !U || !V || !Ur || !Vr) { set_err("null argument"); return OCTANE_EINVAL; }
+    if (p->doCTH && (!d_cth || !d_ctp)) { set_err("doCTH needs cth and ctp"); return OCTANE_EINVAL; }
+    if (c->comm.world > 1) { set_err("context is banded: use the band entry points"); return OCTANE_EINVAL; }
+    begin_call(c);
+    int rc = solve_dev(c, d_img1, d_img2, nx, ny, nc, p, d_u, d_v);
+    if (rc) return rc;
+    if (p->doCTH) {                            // src/oct_optical_flow.cc:71-88
+        launch_ctp_pack(d_cth, d_ctp, (size_t)nx * ny, p->ir == 1, c->stream);
+        c->launches++;
+    }
+    return pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, 0, ny, p, U, V, Ur, Vr);
+}
+
 int octane_pix2uv(octane_ctx* c, const octane_nav* nav, double t1, double t2, const float* u, const float* v,
                   int nx, int ny, const octane_params* p, short* U, short* V, short* Ur, short* Vr, float* dT)
 {
@@ -937,15 +965,20 @@ int octane_optical_flow(octane_ctx* c, const float* img1, const float* img2, con
         c->launches++;
         CUDA_OK(cudaMemcpyAsync(ctp, d_s + 4 * n, sb, cudaMemcpyDeviceToHost, c->stream));
     }
+    // the pixel displacements are final: their copy back runs on the second stream under the
+    // navigation kernel (with pinned host buffers; pageable ones simply serialise)
+    CUDA_OK(cudaEventRecord(c->ev_stage, c->stream));
+    CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_stage, 0));
     int nrc = pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, 0, ny, p, d_s, d_s + n, d_s + 2 * n, d_s + 3 * n);
-    if (nrc < 0) return nrc;
-    CUDA_OK(cudaMemcpyAsync(upix, d_u, fb, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaMemcpyAsync(vpix, d_v, fb, cudaMemcpyDeviceToHost, c->stream));
+    if (nrc < 0) { cudaStreamSynchronize(c->copy_stream); return nrc; }
+    CUDA_OK(cudaMemcpyAsync(upix, d_u, fb, cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_OK(cudaMemcpyAsync(vpix, d_v, fb, cudaMemcpyDeviceToHost, c->copy_stream));
     CUDA_OK(cudaMemcpyAsync(U, d_s, sb, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaMemcpyAsync(V, d_s + n, sb, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaMemcpyAsync(Ur, d_s + 2 * n, sb, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaMemcpyAsync(Vr, d_s + 3 * n, sb, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->copy_stream));
     if (dT) *dT = (float)(t2 - t1);
     return nrc;
 }
@@ -1008,6 +1041,47 @@ int octane_navcal(octane_ctx* c, const short* rad, const short* x, const short* 
     rc = octane_navcal_dev(c, d_rad, d_x, d_y, nx, ny, nav, cal, d_data, d_lat, d_lon);
     if (rc) return rc;
     CUDA_OK(cudaMemcpyAsync(data, d_data, fb, cudaMemcpyDeviceToHost, c->stream));
+    if (lat) {
+        CUDA_OK(cudaMemcpyAsync(lat, d_lat, fb, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(lon, d_lon, fb, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return OCTANE_OK;
+}
+
+int octane_navcal_grid(octane_ctx* c, int grid, const float* data, const short* x, const short* y, int nx, int ny,
+                       const octane_nav* nav, int donav, float* data_out, float* lat, float* lon)
+{
+    if (!c || (grid != 1 && grid != 2) || !data || !x || !y || !nav || !data_out || nx <= 0 || ny <= 0 || (!lat != !lon)) {
+        set_err("null or invalid argument");
+        return OCTANE_EINVAL;
+    }
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t n = (size_t)nx * ny, fb = n * sizeof(float);
+    const size_t xb = align_up((size_t)nx * sizeof(short)), yb = align_up((size_t)ny * sizeof(short));
+    int rc = ensure_stage(c, 4 * fb + xb + yb);
+    if (rc) return rc;
+    char* s = c->stage;
+    float* d_in = (float*)s; s += fb;
+    float* d_out = (float*)s; s += fb;
+    float* d_lat = lat ? (float*)s : nullptr; s += fb;
+    float* d_lon = lon ? (float*)s : nullptr; s += fb;
+    short* d_x = (short*)s; s += xb;
+    short* d_y = (short*)s;
+    begin_call(c);
+    CUDA_OK(cudaMemcpyAsync(d_in, data, fb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_x, x, (size_t)nx * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_y, y, (size_t)ny * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+    // the reference's wrappers convert to radians in double and pass floats (oct_polar_navcal_cuda.cu:141-143,
+    // oct_merc_navcal_cuda.cu:122-124)
+    const double PI = 3.14159265359, DTOR = PI / 180.;
+    const float lon0 = (float)((grid == 1 ? nav->lon0 : nav->lon1) * DTOR);
+    const float lat1 = (float)(nav->lat1 * DTOR);
+    launch_navcal_grid(grid, d_in, d_x, d_y, nx, ny, nav->xScale, nav->xOffset, nav->yScale, nav->yOffset, nav->R, lon0, lat1,
+                       donav, d_out, d_lat, d_lon, c->stream);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(data_out, d_out, fb, cudaMemcpyDeviceToHost, c->stream));
     if (lat) {
         CUDA_OK(cudaMemcpyAsync(lat, d_lat, fb, cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaMemcpyAsync(lon, d_lon, fb, cudaMemcpyDeviceToHost, c->stream));

@@ -131,6 +131,71 @@ void launch_uv2pix(float* u, float* v, const float* lat, const float* lon, const
 }
 
 
+// ---- lat/lon of the two projected grids the reference also ingests: orthographic polar
+// (octpolarnavcalcuda, src/oct_polar_navcal_cuda.cu:12-66) and spherical Mercator (octmercnavcalcuda,
+// src/oct_merc_navcal_cuda.cu:12-48).  The image passes through unchanged (these files hold floats that
+// are already normalised); lat1 / lon0 arrive in radians, narrowed to float, as the reference's host
+// wrappers pass them (:141-143 / :122-124) -- including the pole test `lat1 > 89.99999`, which the reference
+// applies to the radian value and which therefore never fires.
+template <int GRID>   // 1 polar, 2 Mercator
+__global__ void __launch_bounds__(256)
+k_navcal_grid(const float* __restrict__ data2, const short* __restrict__ x, const short* __restrict__ y, int nx, int ny,
+              float xScale, float xOffset, float yScale, float yOffset, float R, float lon0, float lat1, int donav,
+              float* __restrict__ data3, float* __restrict__ lat, float* __restrict__ lon)
+{
+    const double PI = 3.14159265359;
+    const double DTOR = PI / 180.;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= nx || j >= ny) return;
+    const size_t lxyz = (size_t)j * nx + i;
+    double xVal = x[i] * xScale + xOffset;
+    double yVal = y[j] * yScale + yOffset;
+    float dVal = data2[lxyz];
+    if (lat && lon) {
+        float la, lo;
+        if (donav == 1) {
+            if (GRID == 1) {
+                double rho, c;
+                rho = sqrt(xVal * xVal + yVal * yVal);
+                c = asin(rho / R);
+                if (lat1 > 89.99999) {
+                    lo = lon0 + atan2(xVal, -yVal);
+                } else {
+                    lo = lon0 + atan2(xVal * sin(c), (rho * cos(lat1) * cos(c) - yVal * sin(lat1) * sin(c)));
+                }
+                if (rho > 0.0000001) {
+                    la = asin(cos(c) * sin(lat1) + (yVal * sin(c) * cos(lat1) / rho));
+                } else {
+                    la = lat1;
+                }
+            } else {
+                lo = xVal / R + lon0;
+                la = PI / 2. - 2. * atan(exp(-yVal / R));
+            }
+            la = la / DTOR;
+            lo = lo / DTOR;
+        } else {
+            la = 0.;
+            lo = 0.;
+        }
+        lat[lxyz] = la;
+        lon[lxyz] = lo;
+    }
+    data3[lxyz] = dVal;
+}
+
+void launch_navcal_grid(int grid_kind, const float* data2, const short* x, const short* y, int nx, int ny, float xScale,
+                        float xOffset, float yScale, float yOffset, float R, float lon0_rad, float lat1_rad, int donav,
+                        float* data3, float* lat, float* lon, cudaStream_t st)
+{
+    dim3 grid((nx + 255) / 256, ny);
+    if (grid_kind == 1)
+        k_navcal_grid<1><<<grid, 256, 0, st>>>(data2, x, y, nx, ny, xScale, xOffset, yScale, yOffset, R, lon0_rad, lat1_rad, donav, data3, lat, lon);
+    else
+        k_navcal_grid<2><<<grid, 256, 0, st>>>(data2, x, y, nx, ny, xScale, xOffset, yScale, yOffset, R, lon0_rad, lat1_rad, donav, data3, lat, lon);
+}
+
 // ---- regridding of an ancillary field onto the image grid: oct_zoom_in_float, src/oct_zoom.cc:180-222,
 // with oct_bicubic_float / oct_cell, src/oct_bicubic.cc:12-29,100-150 (bicubic when interp == 1, nearest
 // neighbour otherwise).  The reader uses it for cloud-top heights and extra channels that come on a

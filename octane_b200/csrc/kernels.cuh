@@ -109,6 +109,9 @@ struct Uv2PixParams {
     double secs, req, req2, rpol, rpol2, eval, lam0, pph;
     float xscale, xoffset, yscale, yoffset;
 };
+void launch_navcal_grid(int grid_kind, const float* data2, const short* x, const short* y, int nx, int ny, float xScale,
+                        float xOffset, float yScale, float yOffset, float R, float lon0_rad, float lat1_rad, int donav,
+                        float* data3, float* lat, float* lon, cudaStream_t st);
 void launch_zoom_in_float(const float* in, int nx, int ny, float* out, int nxx, int nyy, int interp, cudaStream_t st);
 void launch_uv2pix(float* u, float* v, const float* lat, const float* lon, const short* xs, const short* ys, int nx,
                    int ny, const Uv2PixParams& q, cudaStream_t st);

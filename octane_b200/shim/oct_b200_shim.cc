@@ -164,3 +164,37 @@ void oct_uv2pix(GOESVar& goesData, float* u, float* v, double t2, OFFlags args)
                       (int)goesData.nav.nx, (int)goesData.nav.ny, &p, u, v) < 0)
         die("oct_uv2pix");
 }
+
+// Ingest of the projected grids (src/oct_polar_navcal_cuda.cu:69, src/oct_merc_navcal_cuda.cu:51): full sector
+// only, as the readers call them (src/oct_fileread.cc:560-567, 728-731).  data2s is zero-filled, xs / ys copied,
+// as the reference wrappers do.
+static void grid_navcal(int grid, float* data2, short* data2s, short* x, short* y, short* xs, short* ys, int nx, int ny,
+                        float* data3, float* lat, float* lon, float xScale, float xOffset, float yScale, float yOffset,
+                        float lon0, float lat1, float R, int donav, long plane_offset, OFFlags args)
+{
+    octane_ctx* c = context_for(args.setdevice);
+    for (long k = 0; k < (long)nx * ny; k++) data2s[k] = 0;
+    for (int i = 0; i < nx; i++) xs[i] = x[i];
+    for (int l = 0; l < ny; l++) ys[l] = y[l];
+    octane_nav nav = {};
+    nav.xScale = xScale; nav.xOffset = xOffset; nav.yScale = yScale; nav.yOffset = yOffset;
+    nav.R = R; nav.lon0 = lon0; nav.lon1 = lon0; nav.lat1 = lat1;
+    if (octane_navcal_grid(c, grid, data2, x, y, nx, ny, &nav, donav, data3 + plane_offset, lat, lon) < 0) die("oct_navcal (grid)");
+}
+
+void oct_polar_navcal_cuda(float* data2, short* data2s, short* x, short* y, short* xs, short* ys, int nx, int ny, int /*minx*/,
+                           int /*maxx*/, int /*miny*/, int /*maxy*/, float* data3, float* lat, float* lon, float xScale,
+                           float xOffset, float yScale, float yOffset, float lon0, float lat1, float R, int donav, int chan,
+                           OFFlags args)
+{
+    grid_navcal(1, data2, data2s, x, y, xs, ys, nx, ny, data3, lat, lon, xScale, xOffset, yScale, yOffset, lon0, lat1, R, donav,
+                (long)(chan - 1) * nx * ny, args);
+}
+
+void oct_merc_navcal_cuda(float* data2, short* data2s, short* x, short* y, short* xs, short* ys, int nx, int ny, int /*minx*/,
+                          int /*maxx*/, int /*miny*/, int /*maxy*/, float* data3, float* lat, float* lon, float xScale,
+                          float xOffset, float yScale, float yOffset, float lon0, float R, int donav, OFFlags args)
+{
+    grid_navcal(2, data2, data2s, x, y, xs, ys, nx, ny, data3, lat, lon, xScale, xOffset, yScale, yOffset, lon0, 0.f, R, donav, 0,
+                args);
+}

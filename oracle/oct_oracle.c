@@ -829,3 +829,40 @@ int oracle_zoom_in_float(const float *in, int nx, int ny, float *out, int nxx, i
     }
     return 0;
 }
+
+/* ---- ingest of the projected grids: octpolarnavcalcuda (src/oct_polar_navcal_cuda.cu:12-66, grid 1) and
+ * octmercnavcalcuda (src/oct_merc_navcal_cuda.cu:12-48, grid 2).  lon0 / lat1 in radians as floats (what the
+ * host wrappers pass, :141-143 / :122-124); sin / cos of the float lat1 resolve to the float overloads on the
+ * device. */
+int oracle_navcal_grid(int grid, const float *data2, const short *x, const short *y, int nx, int ny, float xScale,
+                       float xOffset, float yScale, float yOffset, float R, float lon0, float lat1, int donav,
+                       float *data3, float *lat, float *lon)
+{
+    const double PI = 3.14159265359, DTOR = PI / 180.;
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) {
+            const size_t k = (size_t)j * nx + i;
+            double xVal = fmaf((float)x[i], xScale, xOffset);
+            double yVal = fmaf((float)y[j], yScale, yOffset);
+            float la = 0.f, lo = 0.f;
+            if (donav == 1) {
+                if (grid == 1) {
+                    double rho = sqrt(xVal * xVal + yVal * yVal);
+                    double c = asin(rho / R);
+                    if (lat1 > 89.99999) lo = lon0 + atan2(xVal, -yVal);
+                    else lo = lon0 + atan2(xVal * sin(c), (rho * cosf(lat1) * cos(c) - yVal * sinf(lat1) * sin(c)));
+                    if (rho > 0.0000001) la = asin(cos(c) * sinf(lat1) + (yVal * sin(c) * cosf(lat1) / rho));
+                    else la = lat1;
+                } else {
+                    lo = xVal / R + lon0;
+                    la = PI / 2. - 2. * atan(exp(-yVal / R));
+                }
+                la = la / DTOR;
+                lo = lo / DTOR;
+            }
+            if (lat && lon) { lat[k] = la; lon[k] = lo; }
+            data3[k] = data2[k];
+        }
+    return 0;
+}

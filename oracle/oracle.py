@@ -184,6 +184,35 @@ def uv2pix(nav, t1, t2, lat, lon, x, y, u, v):
     return u, v, rc
 
 
+def navcal_grid(grid, data, x, y, xScale, xOffset, yScale, yOffset, R, lon0_deg, lat1_deg=0.0, donav=1):
+    """grid 1 polar / 2 Mercator; angles in degrees as the readers hold them (converted like the reference's wrappers)"""
+    data = np.ascontiguousarray(data, np.float32); x = np.ascontiguousarray(x, np.int16); y = np.ascontiguousarray(y, np.int16)
+    ny, nx = data.shape
+    L = lib()
+    f = C.c_float
+    L.oracle_navcal_grid.argtypes = [C.c_int, _f32, _i16, _i16, C.c_int, C.c_int, f, f, f, f, f, f, f, C.c_int, _f32, _f32, _f32]
+    DTOR = 3.14159265359 / 180.
+    out = np.zeros((ny, nx), np.float32); lat = np.zeros((ny, nx), np.float32); lon = np.zeros((ny, nx), np.float32)
+    L.oracle_navcal_grid(grid, data, x, y, nx, ny, xScale, xOffset, yScale, yOffset, R, np.float32(np.float32(lon0_deg) * DTOR),
+                         np.float32(np.float32(lat1_deg) * DTOR), donav, out, lat, lon)
+    return out, lat, lon
+
+
+def ref_navcal_grid(grid, data, x, y, xScale, xOffset, yScale, yOffset, R, lon0_deg, lat1_deg=0.0, donav=1, L=None):
+    L = L or ref_cuda()
+    data = np.ascontiguousarray(data, np.float32); x = np.ascontiguousarray(x, np.int16); y = np.ascontiguousarray(y, np.int16)
+    ny, nx = data.shape
+    f = C.c_float
+    L.ref_navcal_grid.argtypes = [C.c_int, _f32, _i16, _i16, C.c_int, C.c_int, f, f, f, f, f, f, f, C.c_int, C.POINTER(RefParams),
+                                  _f32, _f32, _f32]
+    out = np.zeros((ny, nx), np.float32); lat = np.zeros((ny, nx), np.float32); lon = np.zeros((ny, nx), np.float32)
+    rp = ref_params()
+    bad = L.ref_navcal_grid(grid, data, x, y, nx, ny, xScale, xOffset, yScale, yOffset, R, lon0_deg, lat1_deg, donav, C.byref(rp),
+                            out, lat, lon)
+    assert bad == 0
+    return out, lat, lon
+
+
 def zoom_in_float(field, nxx, nyy, interp=1):
     field = np.ascontiguousarray(field, np.float32)
     ny, nx = field.shape

@@ -30,6 +30,10 @@ void oct_variational_optical_flow(Image, Image, float*, float*, float*, int, int
 void oct_pix2uv_cuda(GOESVar&, double, float*, float*, short*, short*, short*, short*, OFFlags);
 int oct_optical_flow(GOESVar&, GOESVar&, OFFlags&);
 void oct_uv2pix(GOESVar&, float*, float*, double, OFFlags);
+void oct_polar_navcal_cuda(float*, short*, short*, short*, short*, short*, int, int, int, int, int, int, float*, float*, float*,
+                           float, float, float, float, float, float, float, int, int, OFFlags);
+void oct_merc_navcal_cuda(float*, short*, short*, short*, short*, short*, int, int, int, int, int, int, float*, float*, float*,
+                          float, float, float, float, float, float, int, OFFlags);
 void oct_navcal_cuda(short*, short*, short*, short*, short*, short*, int, int, int, int, int, int, float*, float*,
                      float*, std::string, int, float, float, float, float, float, float, float, float, float, float,
                      float, float, float, float, float, float, float, float, float, int, OFFlags);
@@ -182,6 +186,27 @@ int ref_navcal(const short* rad, const short* x, const short* y, int nx, int ny,
                     c->maxin, c->minin, c->maxout, c->minout, c->donav, a);
     int bad = std::memcmp(data2s, rad, n * sizeof(short)) != 0 || std::memcmp(xs, x, nx * sizeof(short)) != 0 ||
               std::memcmp(ys, y, ny * sizeof(short)) != 0;
+    delete[] data2s; delete[] xs; delete[] ys;
+    return bad;
+}
+
+// grid 1: oct_polar_navcal_cuda (lon0, lat1 in degrees), grid 2: oct_merc_navcal_cuda (lon0 in degrees)
+int ref_navcal_grid(int grid, const float* data2, const short* x, const short* y, int nx, int ny, float xScale, float xOffset,
+                    float yScale, float yOffset, float R, float lon0, float lat1, int donav, const RefParams* p,
+                    float* data3, float* lat, float* lon)
+{
+    OFFlags a; defaults(a, p);
+    const size_t n = (size_t)nx * ny;
+    short* data2s = new short[n];
+    short* xs = new short[nx];
+    short* ys = new short[ny];
+    if (grid == 1)
+        oct_polar_navcal_cuda(const_cast<float*>(data2), data2s, const_cast<short*>(x), const_cast<short*>(y), xs, ys, nx, ny, 0, nx,
+                              0, ny, data3, lat, lon, xScale, xOffset, yScale, yOffset, lon0, lat1, R, donav, 1, a);
+    else
+        oct_merc_navcal_cuda(const_cast<float*>(data2), data2s, const_cast<short*>(x), const_cast<short*>(y), xs, ys, nx, ny, 0, nx,
+                             0, ny, data3, lat, lon, xScale, xOffset, yScale, yOffset, lon0, R, donav, a);
+    int bad = std::memcmp(xs, x, nx * sizeof(short)) != 0 || std::memcmp(ys, y, ny * sizeof(short)) != 0;
     delete[] data2s; delete[] xs; delete[] ys;
     return bad;
 }

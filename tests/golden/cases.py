@@ -146,3 +146,23 @@ def check_latlon(lat, lon, wlat, wlon, r2):
         d = np.abs(a - b)
         assert d[inner].max(initial=0) <= 3.1e-5, d[inner].max(initial=0)
         assert d[outer].max(initial=0) <= 2e-3, d[outer].max(initial=0)
+
+
+# ---- ingest of the projected grids (oct_polar_navcal_cuda / oct_merc_navcal_cuda) ------------------
+GRIDNAV = {
+    "gridnav_polar": dict(grid=1, nx=90, ny=110, xScale=1000.0, xOffset=-45000.0, yScale=-1000.0, yOffset=55000.0,
+                          R=6371228.0, lon0=-150.0, lat1=75.0),
+    "gridnav_polar_origin": dict(grid=1, nx=41, ny=41, xScale=1000.0, xOffset=-20000.0, yScale=-1000.0, yOffset=20000.0,
+                                 R=6371228.0, lon0=30.0, lat1=90.0),       # passes through rho = 0
+    "gridnav_merc": dict(grid=2, nx=110, ny=70, xScale=2000.0, xOffset=-110000.0, yScale=-2000.0, yOffset=4100000.0,
+                         R=6371228.0, lon0=-95.0, lat1=0.0),
+    "gridnav_merc_nonav": dict(grid=2, nx=32, ny=24, xScale=2000.0, xOffset=0.0, yScale=-2000.0, yOffset=100000.0,
+                               R=6371228.0, lon0=10.0, lat1=0.0, donav=0),
+}
+
+
+def gridnav_inputs(c):
+    nx, ny = c["nx"], c["ny"]
+    y, x = np.mgrid[0:ny, 0:nx].astype(np.float32)
+    data = (120.0 + 90.0 * np.sin(x / 7.0) * np.cos(y / 5.0)).astype(np.float32)
+    return data, np.arange(nx, dtype=np.int16), np.arange(ny, dtype=np.int16)

@@ -22,6 +22,7 @@ from oracle import oracle as O  # noqa: E402
 
 def ingest(out):
     """fixtures of the ingest stage (oct_navcal_cuda) and the first-guess conversion (oct_uv2pix)"""
+    out_dir = out
     made = {}
     for name, c in cases.INGEST.items():
         rad, xc, yc, kw, dt = cases.ingest_inputs(c)
@@ -32,6 +33,13 @@ def ingest(out):
         np.savez_compressed(os.path.join(out, name + ".npz"), rad=rad, x=xc, y=yc, data=data, lat=lat, lon=lon)
         print(name, "data range", float(data.min()), float(data.max()), "zeros", int((data == 0).sum()),
               "lat range", float(np.nanmin(lat)), float(np.nanmax(lat)), "nan", int(np.isnan(lat).sum()), flush=True)
+    for name, c in cases.GRIDNAV.items():
+        data, xc, yc = cases.gridnav_inputs(c)
+        out, lat, lon = O.ref_navcal_grid(c["grid"], data, xc, yc, c["xScale"], c["xOffset"], c["yScale"], c["yOffset"], c["R"],
+                                          c["lon0"], c["lat1"], c.get("donav", 1))
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), data=out, lat=lat, lon=lon)
+        print(name, "lat range", float(np.nanmin(lat)), float(np.nanmax(lat)), "lon range", float(np.nanmin(lon)),
+              float(np.nanmax(lon)), "nan", int(np.isnan(lat).sum()), flush=True)
     for name, c in cases.UV2PIX.items():
         lat, lon, xc, yc, kw, dt = made[c["ingest"]]
         kw = dict(kw)

@@ -432,3 +432,61 @@ def test_zoom_in_float_matches_oracle_and_reference(ctx, oracle, dims, interp):
     except OSError:
         pytest.skip("oracle/_ref/libref_cpu.so not built")
     assert np.abs(got - ref).max() <= (0 if interp == 0 else 1e-3)
+
+
+@pytest.mark.parametrize("name", sorted(cases.GRIDNAV))
+def test_gridnav_matches_oracle_and_reference(ctx, oracle, name):
+    c = cases.GRIDNAV[name]
+    data, xc, yc = cases.gridnav_inputs(c)
+    nav = ob.goes_nav(c["xScale"], c["yScale"], c["xOffset"], c["yOffset"])
+    nav.R = c["R"]; nav.lon0 = c["lon0"]; nav.lon1 = c["lon0"]; nav.lat1 = c["lat1"]
+    got = ctx.oct_navcal_grid(c["grid"], data, xc, yc, nav, c.get("donav", 1))
+    want = oracle.navcal_grid(c["grid"], data, xc, yc, c["xScale"], c["xOffset"], c["yScale"], c["yOffset"], c["R"], c["lon0"],
+                              c["lat1"], c.get("donav", 1))
+    refs = [want]
+    g = load_golden(name)
+    refs.append((g["data"], g["lat"], g["lon"]))
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_shim.so")
+    if os.path.exists(so):     # the reference's own C++ signatures, provided by the shim on top of the library
+        shim = oracle.ref_navcal_grid(c["grid"], data, xc, yc, c["xScale"], c["xOffset"], c["yScale"], c["yOffset"], c["R"],
+                                      c["lon0"], c["lat1"], c.get("donav", 1), L=oracle.ref_shim())
+        for a, b in zip(shim, got):
+            assert np.array_equal(a, b, equal_nan=True)
+    for wd, wlat, wlon in refs:
+        assert np.array_equal(got[0], wd)
+        assert np.array_equal(np.isnan(got[1]), np.isnan(wlat))
+        ok = ~np.isnan(wlat)
+        assert np.abs(got[1] - wlat)[ok].max(initial=0) <= 3.1e-5 and np.abs(got[2] - wlon)[ok].max(initial=0) <= 3.1e-5
+
+
+def test_pairs_in_flight_on_several_contexts_match_sequential(ctx):
+    """BASELINE config 5 (independent pairs): the device-buffer dispatcher on three contexts with pairs in flight
+    concurrently gives, bit for bit, what one context gives pair after pair -- and the CTP pack rides along."""
+    import torch
+    nx, ny, npairs = 200, 160, 6
+    xs, ys, xo, yo, dt = S.SECTORS["meso_2km"]
+    nav = ob.goes_nav(xs, ys, xo, yo)
+    p = ob.default_params(doCTH=1)
+    yy, xx = np.mgrid[0:ny, 0:nx].astype(np.float32)
+    cth = (7500.0 + 7400.0 * np.sin(xx / 40.0) * np.cos(yy / 30.0)).astype(np.float32)
+    pairs = [S.make_pair(nx, ny, 200 + k)[:2] for k in range(npairs)]
+    seq = [ctx.oct_optical_flow(a, b, nav, 0.0, dt, p, cth=cth) for a, b in pairs]
+    ctxs = [ob.Context(0) for _ in range(3)]
+    d_cth = dev(cth)
+    d_pairs = [(dev(a), dev(b)) for a, b in pairs]
+    outs = [dict(u=torch.zeros((ny, nx), device="cuda"), v=torch.zeros((ny, nx), device="cuda"),
+                 s=[torch.zeros((ny, nx), dtype=torch.int16, device="cuda") for _ in range(5)]) for _ in pairs]
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(d_pairs):
+        o = outs[i]
+        ctxs[i % 3].oct_optical_flow_dev(a, b, nav, 0.0, dt, p, o["u"], o["v"], *o["s"][:4], cth=d_cth, ctp=o["s"][4],
+                                         sync_torch=False)
+    for c in ctxs:
+        c.synchronize()
+    for i, want in enumerate(seq):
+        o = outs[i]
+        assert np.array_equal(o["u"].cpu().numpy(), want["uPix"]) and np.array_equal(o["v"].cpu().numpy(), want["vPix"])
+        for k, key in enumerate(("uVal", "vVal", "uVal2", "vVal2", "CTP")):
+            assert np.array_equal(o["s"][k].cpu().numpy(), want[key]), key
+    for c in ctxs:
+        c.close()
