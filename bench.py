@@ -337,7 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="fulldisk", choices=sorted(WORKLOADS) + ["custom", "batch64"])
-    ap.add_argument("--streams", type=int, default=4, help="batch64: contexts (pairs in flight) per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="batch64: contexts (pairs in flight) per GPU")
     ap.add_argument("--size", default=None, help="developer: NXxNY scene instead of a named workload (conus sector)")
     ap.add_argument("--seed", type=int, default=4)
     ap.add_argument("--ref-size", type=int, default=1000, help="crop edge of the --impl reference sample")
@@ -537,7 +537,7 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dom)
+            traffic = json.load(f).get(args.workload, {}).get(dom)     # bytes per launch (ncu, see the file's note)
     except Exception:
         pass
     line = {
@@ -551,7 +551,9 @@ def main():
                          else "working set of the coarse levels fits L2; inputs re-read from HBM each step"},
         "clocks": clocks, "gpu_launches": launches * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": ach / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
+                     "algorithmic_bytes_per_launch": (B_PASS2 if dom == "pcg_pass2" else b1) * float(st.finest_pixels),
+                     "peak_source": peak_src,
                      "bytes_per_pixel_per_launch": B_PASS2 if dom == "pcg_pass2" else b1,
                      "pixels_per_launch": int(st.finest_pixels),
                      "pass1": {"GB/s": k1, "avg_ms": st.finest_pass1_ms}, "pass2": {"GB/s": k2, "avg_ms": st.finest_pass2_ms},

@@ -35,9 +35,9 @@ def ingest(out):
               "lat range", float(np.nanmin(lat)), float(np.nanmax(lat)), "nan", int(np.isnan(lat).sum()), flush=True)
     for name, c in cases.GRIDNAV.items():
         data, xc, yc = cases.gridnav_inputs(c)
-        out, lat, lon = O.ref_navcal_grid(c["grid"], data, xc, yc, c["xScale"], c["xOffset"], c["yScale"], c["yOffset"], c["R"],
+        gout, lat, lon = O.ref_navcal_grid(c["grid"], data, xc, yc, c["xScale"], c["xOffset"], c["yScale"], c["yOffset"], c["R"],
                                           c["lon0"], c["lat1"], c.get("donav", 1))
-        np.savez_compressed(os.path.join(out_dir, name + ".npz"), data=out, lat=lat, lon=lon)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), data=gout, lat=lat, lon=lon)
         print(name, "lat range", float(np.nanmin(lat)), float(np.nanmax(lat)), "lon range", float(np.nanmin(lon)),
               float(np.nanmax(lon)), "nan", int(np.isnan(lat).sum()), flush=True)
     for name, c in cases.UV2PIX.items():
