@@ -11,7 +11,7 @@
 // Differences from the reference, all forced by this image having no netcdf-cxx4 / HDF5:
 //   * files are classic NetCDF (CDF-1 / CDF-2), read and written by csrc/cdf.cc; the schema
 //     (dimension / variable / attribute names, types, order) is the reference's;
-//   * -Polar / -Merc readers, -sosm, -srsal, -interp and the DOWN-scaling of an extra channel or a
+//   * -sosm, -srsal, -interp, extra channels / first guess on the -Polar / -Merc grids and the DOWN-scaling of an extra channel or a
 //     cloud-top-height field that is finer than channel 1 (oct_zoom_out_float) are not built (SURVEY.md
 //     section 2: off the variational GOES path); the program says so and stops instead of silently doing
 //     less.  Coarser fields are brought up with octane_zoom_in_float (oct_zoom_in_float).
@@ -56,6 +56,9 @@ struct Scene {                 // the parts of GOESVar / GOESNAVVar the GOES pat
     float xScale = 0, xOffset = 0, yScale = 0, yOffset = 0, radScale = 0, radOffset = 0;
     float req = 0, rpol = 0, pph = 0, lam0 = 0, lpo = 0, lat0 = 0, inverse = 0, gipVal = 0;
     float fk1 = 0, fk2 = 0, bc1 = 0, bc2 = 0, kap1 = 0;
+    // -Polar / -Merc files: float image, grid constants of the "grid_mapping" variable
+    std::vector<float> radf;
+    float lat1 = 0, lon0 = 0, lon1 = 0, R = 0;
 };
 
 void usage()
@@ -130,6 +133,37 @@ bool read_goes(const std::string& path, Scene& s, std::string* err)
     s.rad.resize(nx * ny); s.x.resize(nx); s.y.resize(ny);
     if (f.get_short(rad, s.rad.data()) || f.get_short(xv, s.x.data()) || f.get_short(yv, s.y.data()) ||
         f.get_double(tv, &s.t) || f.get_int(bv, &s.band)) { *err = f.error(); return false; }
+    return true;
+}
+
+// oct_polarread / oct_mercread, src/oct_fileread.cc:418-752: float Rad, short x / y with scale and offset,
+// t, and the grid constants as attributes of the variable "grid_mapping" (polar: lat1, lon0, R; Mercator: lon1, R)
+bool read_grid(const std::string& path, bool polar, Scene& s, std::string* err)
+{
+    cdf::Reader f;
+    if (f.open(path)) { *err = f.error(); return false; }
+    uint64_t nx = 0, ny = 0;
+    if (f.dim_len("x", &nx) || f.dim_len("y", &ny)) { *err = path + ": no x / y dimension"; return false; }
+    s.nx = (int)nx; s.ny = (int)ny;
+    const cdf::Var *rad = f.var("Rad"), *xv = f.var("x"), *yv = f.var("y"), *tv = f.var("t"), *gm = f.var("grid_mapping");
+    if (!rad || !xv || !yv || !tv || !gm) { *err = path + ": Rad, x, y, t or grid_mapping missing"; return false; }
+    if (rad->nelems != nx * ny || xv->nelems != nx || yv->nelems != ny) { *err = path + ": variable shapes do not match the dimensions"; return false; }
+    bool ok = att_f(yv, "scale_factor", &s.yScale, err) && att_f(yv, "add_offset", &s.yOffset, err) &&
+              att_f(xv, "scale_factor", &s.xScale, err) && att_f(xv, "add_offset", &s.xOffset, err) && att_f(gm, "R", &s.R, err);
+    if (ok && polar) ok = att_f(gm, "lat1", &s.lat1, err) && att_f(gm, "lon0", &s.lon0, err);
+    if (ok && !polar) ok = att_f(gm, "lon1", &s.lon1, err);
+    if (!ok) { *err = path + ": " + *err; return false; }
+    const cdf::Att* tu = tv->att("units");
+    if (!tu) { *err = path + ": t:units missing"; return false; }
+    s.tUnits = tu->as_text();
+    float gv = 0.f;
+    f.get_float(gm, &gv);
+    s.gipVal = gv;
+    s.radf.resize(nx * ny); s.x.resize(nx); s.y.resize(ny);
+    if (f.get_float(rad, s.radf.data()) || f.get_short(xv, s.x.data()) || f.get_short(yv, s.y.data()) || f.get_double(tv, &s.t)) {
+        *err = f.error();
+        return false;
+    }
     return true;
 }
 
@@ -298,6 +332,82 @@ bool write_goes(const std::string& path, const Scene& s, const Flags& a, const o
     return true;
 }
 
+// oct_polarwrite (src/oct_filewrite.cc:353-558) and oct_mercwrite (:560-705).  Both declare U and V as doubles:
+// the polar file holds the pixel displacements uPix / vPix there, the Mercator file the navigated shorts
+// (scale_factor 0.01); the solver settings are written for the Zimmer solver only (oftype == 1).
+bool write_grid(const std::string& path, bool polar, const Scene& s, const Flags& a, float dT, const short* U, const short* V,
+                const float* upix, const float* vpix, std::string* err)
+{
+    using cdf::Att;
+    cdf::Writer w;
+    if (w.create(path)) { *err = w.error(); return false; }
+    const int xd = w.add_dim("x", s.nx), yd = w.add_dim("y", s.ny);
+    const int xv = w.add_var("x", cdf::SHORT, { xd }), yv = w.add_var("y", cdf::SHORT, { yd });
+    w.put_att(xv, Att::f32("scale_factor", s.xScale)); w.put_att(xv, Att::f32("add_offset", s.xOffset));
+    w.put_att(yv, Att::f32("scale_factor", s.yScale)); w.put_att(yv, Att::f32("add_offset", s.yOffset));
+    const int tv = w.add_var("t", cdf::DOUBLE, {});
+    w.put_att(tv, Att::text("standard_name", "time"));
+    w.put_att(tv, Att::text("units", s.tUnits));
+    w.put_att(tv, Att::text("axis", "T"));
+    w.put_att(tv, Att::text("bounds", "time_bounds"));
+    w.put_att(tv, Att::text("long_name", "J2000 epoch mid-point between the start and end image scan in seconds"));
+    const std::vector<int> yx = { yd, xd };
+    const int uV = w.add_var("U", cdf::DOUBLE, yx), vV = w.add_var("V", cdf::DOUBLE, yx);
+    int upV = -1, vpV = -1, radV = -1;
+    if (a.pixuv == 1) { upV = w.add_var("Upix", cdf::FLOAT, yx); vpV = w.add_var("Vpix", cdf::FLOAT, yx); }
+    if (a.outrad) radV = w.add_var("Rad", cdf::FLOAT, yx);
+    const int gipV = w.add_var(polar ? "polar_imager_projection" : "merc_imager_projection", cdf::INT, {});
+    const int ofV = w.add_var("optical_flow_settings", cdf::INT, {});
+    const char* gm = polar ? "polar_orthonormal" : "Mercator Sphere";
+    w.put_att(uV, Att::text("long_name", "U")); w.put_att(uV, Att::text("grid_mapping", gm));
+    if (!polar) w.put_att(uV, Att::f32("scale_factor", 0.01f));
+    w.put_att(uV, Att::text("units", a.pixuv == 0 ? "meters per second" : "x-pixels"));
+    w.put_att(vV, Att::text("long_name", "V")); w.put_att(vV, Att::text("grid_mapping", gm));
+    if (!polar) w.put_att(vV, Att::f32("scale_factor", 0.01f));
+    w.put_att(vV, Att::text("units", a.pixuv == 1 ? "y-pixels" : "meters per second"));
+    if (a.outrad) { w.put_att(radV, Att::text("long_name", "Rad")); w.put_att(radV, Att::text("grid_mapping", gm)); }
+    if (polar) {
+        w.put_att(gipV, Att::text("long_name", "Polar_Orthonormal_Grid"));
+        w.put_att(gipV, Att::text("grid_mapping_name", "polar"));
+        w.put_att(gipV, Att::f64("lat1", (double)s.lat1));
+        w.put_att(gipV, Att::f64("lon0", (double)s.lon0));
+    } else {
+        w.put_att(gipV, Att::text("long_name", "Mercator_Grid"));
+        w.put_att(gipV, Att::text("grid_mapping_name", "Mercator"));
+        w.put_att(gipV, Att::f64("lon1", (double)s.lon1));
+    }
+    w.put_att(gipV, Att::f64("R", (double)s.R));
+    w.put_att(ofV, Att::text("long_name", "Optical Flow Settings"));
+    w.put_att(ofV, Att::text("key", "1 = Modified Sun (2014), 2 = Farneback, 3 = Brox (2004)"));
+    if (a.oftype == 1) {
+        w.put_att(ofV, Att::f64("lambda", a.lambda)); w.put_att(ofV, Att::f64("lambdac", a.lambdac));
+        w.put_att(ofV, Att::f64("alpha", a.alpha)); w.put_att(ofV, Att::f64("filtsigma", a.filtsigma));
+        w.put_att(ofV, Att::f64("ScaleF", a.scaleF));
+        w.put_att(ofV, Att::i32("K_Iterations", a.kiters)); w.put_att(ofV, Att::i32("L_Iterations", a.liters));
+        w.put_att(ofV, Att::i32("M_Iterations", a.miters)); w.put_att(ofV, Att::i32("CG_Iterations", a.cgiters));
+        w.put_att(ofV, Att::f32("NormMax", a.NormMax)); w.put_att(ofV, Att::f32("NormMin", a.NormMin));
+        w.put_att(ofV, Att::i32("dofirstguess", a.dofirstguess));
+    }
+    w.put_att(ofV, Att::f32("dt_seconds", dT));
+    if (w.enddef()) { *err = w.error(); return false; }
+    const uint64_t n = (uint64_t)s.nx * s.ny;
+    std::vector<double> du(n), dv(n);
+    for (uint64_t k = 0; k < n; k++) { du[k] = polar ? (double)upix[k] : (double)U[k]; dv[k] = polar ? (double)vpix[k] : (double)V[k]; }
+    int rc = 0;
+    rc |= w.put_var(xv, s.x.data(), s.nx);
+    rc |= w.put_var(yv, s.y.data(), s.ny);
+    rc |= w.put_var(tv, &s.t, 1);
+    rc |= w.put_var(uV, du.data(), n);
+    rc |= w.put_var(vV, dv.data(), n);
+    if (a.pixuv == 1) { rc |= w.put_var(upV, upix, n); rc |= w.put_var(vpV, vpix, n); }
+    if (a.outrad) rc |= w.put_var(radV, s.data.data(), n);
+    const int gv = (int)s.gipVal, ofv = a.oftype;
+    rc |= w.put_var(gipV, &gv, 1);
+    rc |= w.put_var(ofV, &ofv, 1);
+    if (rc || w.close()) { *err = w.error(); return false; }
+    return true;
+}
+
 int fail(const std::string& msg)
 {
     fprintf(stderr, "octane: %s\n", msg.c_str());
@@ -388,7 +498,8 @@ int main(int argc, char* argv[])
                args.dopolar, args.domerc, args.dososm, args.docorn);
         return 0;
     }
-    if (args.dopolar || args.domerc) return fail("-Polar / -Merc readers are not part of this build (GOES fixed-grid path only)");
+    if ((args.dopolar || args.domerc) && (args.doc2 || args.doc3 || args.dofirstguess))
+        return fail("extra channels / first guess with -Polar / -Merc are not part of this build");
     if (args.dososm) return fail("-sosm (CPU patch-match solver) is not part of this build");
     if ((args.doc2 && fc22 == "none") || (args.doc3 && fc32 == "none")) {       // src/main.cc:352-361
         printf("Missing files for second / third channel...stopping \n");
@@ -400,6 +511,54 @@ int main(int argc, char* argv[])
     printf("Here are the file names being used: \nFile 1 : %s\nFile 2 : %s\n", f1.c_str(), f2.c_str());
     std::string err;
     Scene g1, g2;
+    if (args.dopolar || args.domerc) {
+        // ---- projected grids: oct_polarread / oct_mercread -> ingest -> flow -> pix2uv (polar / Mercator branch)
+        const bool polar = args.dopolar == 1;
+        if (!read_grid(f1, polar, g1, &err) || !read_grid(f2, polar, g2, &err)) return fail(err);
+        if (g1.nx != g2.nx || g1.ny != g2.ny) return fail("the two images differ in size");
+        const int gnx = g1.nx, gny = g1.ny;
+        const size_t gn = (size_t)gnx * gny;
+        const std::string gout = outdir + (polar ? "outfile_polar.nc" : "outfile_merc.nc");      // main.cc:442-444
+        std::vector<short> U(gn, 0), V(gn, 0), Ur(gn, 0), Vr(gn, 0);
+        std::vector<float> up(gn, 0.f), vp(gn, 0.f);
+        float dT = (float)(g2.t - g1.t);
+        if (args.dry_run) {
+            g1.data = g1.radf;
+            if (!write_grid(gout, polar, g1, args, dT, U.data(), V.data(), up.data(), vp.data(), &err)) return fail(err);
+            printf("%s written (dry run: no motion computed)\n", gout.c_str());
+            return 0;
+        }
+        octane_ctx* gctx = nullptr;
+        int grc = octane_ctx_create(&gctx, args.setdevice);
+        if (grc == OCTANE_ENODEV) { printf("No gpus available for use, exiting\n"); return 0; }
+        if (grc) return fail(octane_last_error());
+        octane_nav gnav;
+        memset(&gnav, 0, sizeof gnav);
+        gnav.xScale = g1.xScale; gnav.xOffset = g1.xOffset; gnav.yScale = g1.yScale; gnav.yOffset = g1.yOffset;
+        gnav.g2xOffset = g1.xOffset; gnav.g2yOffset = g1.yOffset;      // main.cc:400-405: the sector guard is GOES-only
+        gnav.lat1 = g1.lat1; gnav.lon0 = g1.lon0; gnav.lon1 = g1.lon1; gnav.R = g1.R;
+        Scene* pair[2] = { &g1, &g2 };
+        for (int k = 0; k < 2; k++) {
+            Scene& sc = *pair[k];
+            sc.data.resize(gn); sc.lat.resize(gn); sc.lon.resize(gn);
+            if (octane_navcal_grid(gctx, polar ? 1 : 2, sc.radf.data(), sc.x.data(), sc.y.data(), gnx, gny, &gnav, k == 0,
+                                   sc.data.data(), sc.lat.data(), sc.lon.data()) < 0)
+                return fail(octane_last_error());
+        }
+        octane_params gp;
+        octane_params_default(&gp);
+        gp.alpha = args.alpha; gp.lambda = args.lambda; gp.lambdac = args.lambdac; gp.scaleF = args.scaleF; gp.scsig = args.scsig;
+        gp.kiters = args.kiters; gp.liters = args.liters; gp.cgiters = args.cgiters; gp.dozim = args.dozim;
+        gp.setdevice = args.setdevice; gp.pixuv = args.pixuv; gp.dopolar = args.dopolar; gp.domerc = args.domerc;
+        grc = octane_optical_flow(gctx, g1.data.data(), g2.data.data(), nullptr, gnx, gny, 1, &gnav, g1.t, g2.t, &gp, up.data(),
+                                  vp.data(), U.data(), V.data(), Ur.data(), Vr.data(), nullptr, &dT);
+        if (grc < 0) return fail(octane_last_error());
+        if (!write_grid(gout, polar, g1, args, dT, U.data(), V.data(), up.data(), vp.data(), &err)) return fail(err);
+        printf("%s written\n", gout.c_str());
+        octane_ctx_destroy(gctx);
+        printf("OCTANE completed, exiting\n");
+        return 0;
+    }
     if (!read_goes(f1, g1, &err) || !read_goes(f2, g2, &err)) return fail(err);
     if (g1.nx != g2.nx || g1.ny != g2.ny) return fail("the two images differ in size");
     const int nx = g1.nx, ny = g1.ny;

@@ -43,3 +43,24 @@ def counts_from_image(img, maxin, minin, radScale, radOffset):
     """inverse of the ingest normalisation: brightness 0..255 -> radiance -> short counts"""
     radv = img.astype(np.float64) / 255.0 * (maxin - minin) + minin
     return np.clip(np.rint((radv - radOffset) / radScale), -32768, 32767).astype(np.int16)
+
+
+def write_grid_file(path, rad, x, y, t, xScale, xOffset, yScale, yOffset, R, lat1=None, lon0=None, lon1=None):
+    """-Polar / -Merc shaped file (reference oct_polarread / oct_mercread, src/oct_fileread.cc:418-752):
+    float Rad, grid constants on the variable grid_mapping"""
+    ny, nx = rad.shape
+    f = netcdf_file(path, "w", version=2)
+    f.createDimension("y", ny); f.createDimension("x", nx)
+    v = f.createVariable("Rad", "f", ("y", "x")); v[:] = rad.astype(np.float32)
+    v = f.createVariable("x", "h", ("x",)); v[:] = x
+    v.scale_factor = np.float32(xScale); v.add_offset = np.float32(xOffset)
+    v = f.createVariable("y", "h", ("y",)); v[:] = y
+    v.scale_factor = np.float32(yScale); v.add_offset = np.float32(yOffset)
+    v = f.createVariable("t", "d", ()); v.data[...] = t; v.units = "seconds since 2000-01-01 12:00:00"
+    v = f.createVariable("grid_mapping", "i", ()); v.data[...] = 7
+    v.R = np.float32(R)
+    if lat1 is not None:
+        v.lat1 = np.float32(lat1); v.lon0 = np.float32(lon0)
+    if lon1 is not None:
+        v.lon1 = np.float32(lon1)
+    f.close()

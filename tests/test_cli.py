@@ -193,3 +193,68 @@ def test_cli_end_to_end_matches_the_library(tmp_path, ctx, mode):
     assert int(v["optical_flow_settings"].dofirstguess) == int(mode == "firstguess")
     assert np.abs(v["U_raw"][:].astype(int)).max() > 20        # a real flow field came out (>0.2 px)
     f.close()
+
+
+def _grid_files(tmp, kind, nx=128, ny=96):
+    c = cases.GRIDNAV["gridnav_polar" if kind == "polar" else "gridnav_merc"]
+    i1, i2, _, _ = S.make_pair(nx, ny, 41)
+    xc = np.arange(nx, dtype=np.int16); yc = np.arange(ny, dtype=np.int16)
+    f1, f2 = os.path.join(tmp, kind + "1.nc"), os.path.join(tmp, kind + "2.nc")
+    kw = dict(lat1=c["lat1"], lon0=c["lon0"]) if kind == "polar" else dict(lon1=c["lon0"])
+    G.write_grid_file(f1, i1, xc, yc, 5000.0, c["xScale"], c["xOffset"], c["yScale"], c["yOffset"], c["R"], **kw)
+    G.write_grid_file(f2, i2, xc, yc, 5000.0 + 3600.0, c["xScale"], c["xOffset"], c["yScale"], c["yOffset"], c["R"], **kw)
+    return dict(f1=f1, f2=f2, i1=i1, i2=i2, xc=xc, yc=yc, c=c, nx=nx, ny=ny)
+
+
+@pytest.mark.parametrize("kind", ["polar", "merc"])
+def test_projected_grid_layout(tmp_path, kind):
+    """-Polar / -Merc dry run: outfile_polar.nc / outfile_merc.nc with the reference's schema
+    (src/oct_filewrite.cc:353-705): U, V declared double, the grid constants on *_imager_projection"""
+    from scipy.io import netcdf_file
+    tmp = str(tmp_path)
+    d = _grid_files(tmp, kind)
+    flag = "-Polar" if kind == "polar" else "-Merc"
+    run("-i1", d["f1"], "-i2", d["f2"], flag, "-pd", "-o", tmp + "/", "-dry_run")
+    f = netcdf_file(os.path.join(tmp, f"outfile_{kind}.nc"), "r", mmap=False)
+    proj = "polar_imager_projection" if kind == "polar" else "merc_imager_projection"
+    assert list(f.variables) == ["x", "y", "t", "U", "V", "Upix", "Vpix", "Rad", proj, "optical_flow_settings"]
+    v = f.variables
+    assert v["U"].data.dtype == np.dtype(">f8") and v["Rad"].data.dtype == np.dtype(">f4") and v["U"].units == b"x-pixels"
+    assert np.array_equal(v["Rad"][:], d["i1"]) and float(v["t"].getValue()) == 5000.0
+    assert float(v["optical_flow_settings"].dt_seconds) == 3600.0 and int(v["optical_flow_settings"].K_Iterations) == 4
+    if kind == "polar":
+        assert v[proj].grid_mapping_name == b"polar" and float(v[proj].lat1) == d["c"]["lat1"] and float(v[proj].lon0) == d["c"]["lon0"]
+        assert v["U"].grid_mapping == b"polar_orthonormal" and not hasattr(v["U"], "scale_factor")
+    else:
+        assert v[proj].grid_mapping_name == b"Mercator" and float(v[proj].lon1) == d["c"]["lon0"]
+        assert abs(float(v["U"].scale_factor) - 0.01) < 1e-9
+    assert float(v[proj].R) == float(np.float32(d["c"]["R"]))
+    f.close()
+    r = run("-i1", d["f1"], "-i2", d["f2"], flag, "-firstguess", "x.nc", "-dry_run", check=False)
+    assert r.returncode == 1 and "not part of this build" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["polar", "merc"])
+def test_cli_projected_grids_end_to_end(tmp_path, ctx, kind):
+    from scipy.io import netcdf_file
+    tmp = str(tmp_path)
+    d = _grid_files(tmp, kind)
+    c = d["c"]
+    run("-i1", d["f1"], "-i2", d["f2"], "-Polar" if kind == "polar" else "-Merc", "-o", tmp + "/")
+    nav = ob.goes_nav(c["xScale"], c["yScale"], c["xOffset"], c["yOffset"])
+    nav.R = float(np.float32(c["R"])); nav.lon0 = c["lon0"] if kind == "polar" else 0.0
+    nav.lon1 = 0.0 if kind == "polar" else c["lon0"]; nav.lat1 = c["lat1"] if kind == "polar" else 0.0
+    grid = 1 if kind == "polar" else 2
+    img1, _, _ = ctx.oct_navcal_grid(grid, d["i1"], d["xc"], d["yc"], nav, 1)
+    img2, _, _ = ctx.oct_navcal_grid(grid, d["i2"], d["xc"], d["yc"], nav, 0)
+    p = ob.default_params(dopolar=int(kind == "polar"), domerc=int(kind == "merc"))
+    want = ctx.oct_optical_flow(img1, img2, nav, 5000.0, 8600.0, p)
+    f = netcdf_file(os.path.join(tmp, f"outfile_{kind}.nc"), "r", mmap=False)
+    v = f.variables
+    if kind == "polar":     # the polar file carries the pixel displacements in its double U / V
+        assert np.array_equal(v["U"][:], want["uPix"].astype(np.float64)) and np.array_equal(v["V"][:], want["vPix"].astype(np.float64))
+    else:
+        assert np.array_equal(v["U"][:], want["uVal"].astype(np.float64)) and np.array_equal(v["V"][:], want["vVal"].astype(np.float64))
+    assert np.abs(want["uPix"]).max() > 0.2
+    f.close()
