@@ -37,6 +37,12 @@
  *   octane_zoom_in_float       void oct_zoom_in_float(float*flow,float*flowout,int nx,int ny,int nxx,int nyy,
  *                              int cnum,int interp), src/oct_zoom.cc:180 (cloud-top heights / extra channels
  *                              on a coarser grid, src/oct_fileread.cc:370,796)
+ *   octane_zoom_out_float      void oct_zoom_out_float(float*image,float*imageout,int nx,int ny,double factor,
+ *                              int verb,int cnum), src/oct_zoom.cc:51 (cloud-top heights / extra channels
+ *                              on a FINER grid, src/oct_fileread.cc:379,805); octane_zoom_out_size is
+ *                              oct_zoom_size, src/oct_zoom.cc:12
+ *   octane_srsal*              void oct_srsal_cu(float*upix,float*vpix,float*CTHsub21,int nx,int ny,OFFlags)
+ *                              src/oct_srsal_cuda.cu:73 (-srsal, called by oct_optical_flow.cc:100-105)
  * Image layout everywhere: row-major float32, index i + nx*j (+ nx*ny*c), i = x
  * (fastest), as the reference (src/oct_variational_optical_flow.cu:316-320).
  */
@@ -50,7 +56,7 @@
 extern "C" {
 #endif
 
-#define OCTANE_ABI_VERSION 1
+#define OCTANE_ABI_VERSION 2   /* 2: octane_params.dosrsal appended; zoom-out and srsal entry points */
 
 enum {
     OCTANE_OK = 0,
@@ -84,6 +90,8 @@ typedef struct octane_params {
                           sizes the image-2 warp halo                (64) */
     int doCTH;         /* -i1cth: pack CTP                      (0)   */
     int ir;            /* -ir: CTP = (CTH-300)*100              (0)   */
+    int dosrsal;       /* -srsal: bilateral post-smoothing of the pixel displacements
+                          by the dispatcher, needs cth           (0)   */
 } octane_params;
 
 /* GOESNAVVar subset (double/float split as in the reference: the float fields
@@ -165,7 +173,9 @@ int octane_pix2uv(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
                   short* U, short* V, short* U_raw, short* V_raw, float* dT);
 
 /* Dispatcher: solve + CTP pack + navigation with the flow kept on the device
- * between the two stages.  cth/ctp may be NULL when !p->doCTH. */
+ * between the two stages.  cth/ctp may be NULL when !p->doCTH (cth is also needed by
+ * p->dosrsal, which smooths upix/vpix AFTER the navigation as oct_optical_flow.cc:91-105 does:
+ * U, V, U_raw, V_raw come from the unsmoothed flow). */
 int octane_optical_flow(octane_ctx* ctx, const float* img1, const float* img2, const float* cth,
                         int nx, int ny, int nc, const octane_nav* nav, double t1, double t2,
                         const octane_params* p, float* upix_inout, float* vpix_inout,
@@ -195,6 +205,18 @@ int octane_uv2pix(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
  * interp == 1 (default of the reference, -nncth selects 0 = nearest neighbour). */
 int octane_zoom_in_float(octane_ctx* ctx, const float* in, int nx, int ny, float* out, int nxx, int nyy, int interp);
 
+/* Regrid a FINER ancillary field (nx*ny) down to the image grid: Gaussian blur (sigma = 0.6 sqrt(1/factor^2 - 1),
+ * radius max(5, (int)(2 sigma)), +R tap dropped) and bicubic sampling at (ii/factor, jj/factor), all in double as
+ * the reference's CPU code; factor in (0, 1], >= 0.999999 copies.  out: dense nxx*nyy plane with (nxx, nyy) from
+ * octane_zoom_out_size (the reference stores it at imageout + cnum -- an element, not a plane, offset; placing the
+ * plane is the caller's business here).  Bit-identical to the reference's CPU object. */
+int octane_zoom_out_size(int nx, int ny, double factor, int* nxx, int* nyy);
+int octane_zoom_out_float(octane_ctx* ctx, const float* in, int nx, int ny, float* out, double factor);
+
+/* -srsal: 37 x 37 bilateral filter (spatial sigma 9 px, range sigma 20 in the units of cth) of the pixel
+ * displacements, in place.  nx, ny must exceed 18 (below that the reference's reflected index leaves the array). */
+int octane_srsal(octane_ctx* ctx, float* u_inout, float* v_inout, const float* cth, int nx, int ny);
+
 /* ---- device-pointer entry points (stream-ordered on the ctx stream) ----- */
 /* All pointers are device memory on the context's device, dense (stride nx). */
 int octane_variational_flow_dev(octane_ctx* ctx, const float* d_img1, const float* d_img2,
@@ -214,6 +236,8 @@ int octane_optical_flow_dev(octane_ctx* ctx, const float* d_img1, const float* d
 int octane_navcal_dev(octane_ctx* ctx, const short* d_rad, const short* d_x, const short* d_y, int nx, int ny,
                       const octane_nav* nav, const octane_cal* cal, float* d_data, float* d_lat, float* d_lon);
 int octane_zoom_in_float_dev(octane_ctx* ctx, const float* d_in, int nx, int ny, float* d_out, int nxx, int nyy, int interp);
+int octane_zoom_out_float_dev(octane_ctx* ctx, const float* d_in, int nx, int ny, float* d_out, double factor);
+int octane_srsal_dev(octane_ctx* ctx, float* d_u_inout, float* d_v_inout, const float* d_cth, int nx, int ny);
 int octane_uv2pix_dev(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
                       const float* d_lat, const float* d_lon, const short* d_x, const short* d_y,
                       int nx, int ny, const octane_params* p, float* d_u_inout, float* d_v_inout);

@@ -22,7 +22,8 @@ class Params(C.Structure):
                 ("scaleF", C.c_double), ("scsig", C.c_double),
                 ("kiters", C.c_int), ("liters", C.c_int), ("cgiters", C.c_int), ("dozim", C.c_int),
                 ("setdevice", C.c_int), ("pixuv", C.c_int), ("dopolar", C.c_int), ("domerc", C.c_int),
-                ("first_guess", C.c_int), ("max_disp", C.c_int), ("doCTH", C.c_int), ("ir", C.c_int)]
+                ("first_guess", C.c_int), ("max_disp", C.c_int), ("doCTH", C.c_int), ("ir", C.c_int),
+                ("dosrsal", C.c_int)]
 
 
 class Nav(C.Structure):
@@ -63,6 +64,7 @@ EXPORTS = [
     "octane_variational_flow_dev", "octane_pix2uv_dev", "octane_optical_flow_dev",
     "octane_navcal", "octane_navcal_dev", "octane_band_minmax", "octane_uv2pix", "octane_uv2pix_dev",
     "octane_zoom_in_float", "octane_zoom_in_float_dev", "octane_navcal_grid",
+    "octane_zoom_out_size", "octane_zoom_out_float", "octane_zoom_out_float_dev", "octane_srsal", "octane_srsal_dev",
     "octane_stage_blur_decimate", "octane_stage_gradient", "octane_stage_zoom_in",
     "octane_stage_build", "octane_stage_pcg",
     "octane_band_plan", "octane_comm_unique_id", "octane_comm_init", "octane_comm_rank",
@@ -115,6 +117,11 @@ def load() -> C.CDLL:
     L.octane_navcal_grid.argtypes = [vp, i, vp, vp, vp, i, i, NP, i, vp, vp, vp]
     L.octane_zoom_in_float.argtypes = [vp, vp, i, i, vp, i, i, i]
     L.octane_zoom_in_float_dev.argtypes = [vp, vp, i, i, vp, i, i, i]
+    L.octane_zoom_out_size.argtypes = [i, i, d, ip, ip]
+    L.octane_zoom_out_float.argtypes = [vp, vp, i, i, vp, d]
+    L.octane_zoom_out_float_dev.argtypes = [vp, vp, i, i, vp, d]
+    L.octane_srsal.argtypes = [vp, vp, vp, vp, i, i]
+    L.octane_srsal_dev.argtypes = [vp, vp, vp, vp, i, i]
     L.octane_stage_blur_decimate.argtypes = [vp, vp, i, i, i, f, vp]
     L.octane_stage_gradient.argtypes = [vp, vp, i, i, i, vp, vp]
     L.octane_stage_zoom_in.argtypes = [vp, vp, i, i, i, i, f, vp]

@@ -84,6 +84,16 @@ def level_dims(nx: int, ny: int, p: Optional[Params] = None):
     return out
 
 
+def zoom_out_size(nx: int, ny: int, factor: float):
+    """(nxx, nyy) of oct_zoom_size, src/oct_zoom.cc:12"""
+    L = _lib.load()
+    a, b = C.c_int(), C.c_int()
+    rc = L.octane_zoom_out_size(nx, ny, factor, C.byref(a), C.byref(b))
+    if rc < 0:
+        raise OctaneError(rc, L.octane_last_error().decode())
+    return a.value, b.value
+
+
 def band_plan(nx: int, ny: int, p: Params, rank: int, world: int):
     """(own0, own1, in0, in1): finest rows solved by `rank`, full-res input rows it needs."""
     L = _lib.load()
@@ -328,6 +338,33 @@ class Context:
         out = np.empty((nyy, nxx), np.float32)
         self._check(self._L.octane_zoom_in_float(self._h, _ptr(field), nx, ny, _ptr(out), nxx, nyy, interp))
         return out
+
+    def oct_zoom_out_float(self, field, factor: float):
+        """regrid a FINER field down by `factor` <= 1 (oct_zoom_out_float, src/oct_zoom.cc:51); the output is
+        the dense (nyy, nxx) plane of zoom_out_size"""
+        ny, nx = field.shape
+        nxx, nyy = zoom_out_size(nx, ny, factor)
+        if _is_torch(field):
+            import torch
+            out = torch.empty((nyy, nxx), dtype=torch.float32, device=field.device)
+            self._after_torch()
+            self._check(self._L.octane_zoom_out_float_dev(self._h, _ptr(field), nx, ny, _ptr(out), factor))
+            return out
+        field = np.ascontiguousarray(field, np.float32)
+        out = np.empty((nyy, nxx), np.float32)
+        self._check(self._L.octane_zoom_out_float(self._h, _ptr(field), nx, ny, _ptr(out), factor))
+        return out
+
+    def oct_srsal_cu(self, upix, vpix, cth):
+        """-srsal bilateral post-smoother, in place on upix / vpix (oct_srsal_cu, src/oct_srsal_cuda.cu:73)"""
+        ny, nx = upix.shape
+        if _is_torch(upix):
+            self._after_torch()
+            self._check(self._L.octane_srsal_dev(self._h, _ptr(upix), _ptr(vpix), _ptr(cth), nx, ny))
+            return upix, vpix
+        cth = np.ascontiguousarray(cth, np.float32)
+        self._check(self._L.octane_srsal(self._h, _ptr(upix), _ptr(vpix), _ptr(cth), nx, ny))
+        return upix, vpix
 
     def oct_uv2pix(self, nav: Nav, t1: float, t2: float, lat, lon, x, y, u, v, p: Optional[Params] = None) -> int:
         """u, v: first-guess winds (m/s) in, pixel displacements out (in place).  Returns 1 when the

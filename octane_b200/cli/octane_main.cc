@@ -11,10 +11,12 @@
 // Differences from the reference, all forced by this image having no netcdf-cxx4 / HDF5:
 //   * files are classic NetCDF (CDF-1 / CDF-2), read and written by csrc/cdf.cc; the schema
 //     (dimension / variable / attribute names, types, order) is the reference's;
-//   * -sosm, -srsal, -interp, extra channels / first guess on the -Polar / -Merc grids and the DOWN-scaling of an extra channel or a
-//     cloud-top-height field that is finer than channel 1 (oct_zoom_out_float) are not built (SURVEY.md
+//   * -sosm, -interp and extra channels / first guess on the -Polar / -Merc grids are not built (SURVEY.md
 //     section 2: off the variational GOES path); the program says so and stops instead of silently doing
-//     less.  Coarser fields are brought up with octane_zoom_in_float (oct_zoom_in_float).
+//     less.  Coarser fields are brought up with octane_zoom_in_float (oct_zoom_in_float), finer ones down
+//     with octane_zoom_out_float (oct_zoom_out_float); -srsal runs inside the dispatcher (octane_srsal).
+//   * an extra channel that is FINER than channel 1 lands in its own channel plane; the reference stores
+//     it at an element offset instead (oct_zoom.cc:84) and so overwrites channel 1.
 // Quirks kept: -cgiters is documented but never parsed (:144); -corn leaves docorn = 0 (:270-273);
 // -scsig stores the square (:229); -set_device is 1-based (:313); -normmax/-normmin only change
 // the attribute written, the normalisation always uses the band table (oct_fileread.cc:344-388).
@@ -183,21 +185,34 @@ bool read_plane(const std::string& path, const char* var, int* fx_out, int* fy_o
 }
 
 // Bring a field of size fx*fy onto the nx*ny image grid the way the readers do (oct_fileread.cc:361-380,
-// 794-806): same size -> unchanged (oct_zoom_out_float with factor 1 copies, oct_zoom.cc:79-86); coarser ->
-// oct_zoom_in_float (bicubic, or nearest neighbour with -nncth); finer -> oct_zoom_out_float, not built.
+// 794-806): same size -> unchanged (oct_zoom_out_float with factor 1 copies, oct_zoom.cc:79-86); image wider
+// than the field -> oct_zoom_in_float (bicubic, or nearest neighbour with -nncth); otherwise
+// oct_zoom_out_float with factor nx / fx, after the reference's check that x and y scale alike.
 // ctx == nullptr (dry run): only the same-size case.
 bool regrid(octane_ctx* ctx, const std::string& what, std::vector<float>& field, int fx, int fy, int nx, int ny, int interp,
             std::string* err)
 {
     if (fx == nx && fy == ny) return true;
-    if (fx > nx || fy > ny || !ctx) {
-        *err = what + " is " + std::to_string(fx) + "x" + std::to_string(fy) + ", image is " + std::to_string(nx) + "x" +
-               std::to_string(ny) + (ctx ? "; down-scaling a finer field (oct_zoom_out_float) is not built"
-                                         : "; regridding needs the GPU (not available in a dry run)");
-        return false;
-    }
+    const std::string sizes = what + " is " + std::to_string(fx) + "x" + std::to_string(fy) + ", image is " +
+                              std::to_string(nx) + "x" + std::to_string(ny);
+    if (!ctx) { *err = sizes + "; regridding needs the GPU (not available in a dry run)"; return false; }
     std::vector<float> out((size_t)nx * ny);
-    if (octane_zoom_in_float(ctx, field.data(), fx, fy, out.data(), nx, ny, interp) < 0) { *err = octane_last_error(); return false; }
+    if (nx > fx) {
+        if (ny < fy) { *err = sizes + "; x needs up-scaling and y down-scaling"; return false; }
+        if (octane_zoom_in_float(ctx, field.data(), fx, fy, out.data(), nx, ny, interp) < 0) { *err = octane_last_error(); return false; }
+    } else {
+        const double factor = (double)nx / ((double)fx), factor2 = (double)ny / ((double)fy);
+        if (pow(factor - factor2, 2) > 0.000001) {      // oct_fileread.cc:375-378, 800-804 (the reference exits)
+            *err = sizes + "; x and y dimensions not compatible for scaling (factor not the same)";
+            return false;
+        }
+        int ox = 0, oy = 0;
+        if (octane_zoom_out_size(fx, fy, factor, &ox, &oy) < 0 || ox != nx || oy != ny) {
+            *err = sizes + "; scaled field would be " + std::to_string(ox) + "x" + std::to_string(oy);
+            return false;
+        }
+        if (octane_zoom_out_float(ctx, field.data(), fx, fy, out.data(), factor) < 0) { *err = octane_last_error(); return false; }
+    }
     field.swap(out);
     return true;
 }
@@ -505,7 +520,9 @@ int main(int argc, char* argv[])
         printf("Missing files for second / third channel...stopping \n");
         return 0;
     }
-    if (args.dosrsal) printf("Warning: -srsal smoothing is not part of this build; output is unsmoothed\n");
+    if (args.dosrsal && (args.dopolar || args.domerc)) return fail("-srsal with -Polar / -Merc is not part of this build");
+    // oct_optical_flow.cc:100-105 hands goesData.CTHVal to the smoother whether or not it was read
+    if (args.dosrsal && args.doCTH != 1) return fail("-srsal needs cloud-top heights (-i1cth)");
     if (args.dointerp) printf("Warning: -interp is not part of this build; only outfile.nc is written\n");
 
     printf("Here are the file names being used: \nFile 1 : %s\nFile 2 : %s\n", f1.c_str(), f2.c_str());
@@ -650,7 +667,7 @@ int main(int argc, char* argv[])
     p.alpha = args.alpha; p.lambda = args.lambda; p.lambdac = args.lambdac; p.scaleF = args.scaleF; p.scsig = args.scsig;
     p.kiters = args.kiters; p.liters = args.liters; p.cgiters = args.cgiters; p.dozim = args.dozim;
     p.setdevice = args.setdevice; p.pixuv = args.pixuv; p.doCTH = args.doCTH; p.ir = args.ir;
-    p.first_guess = args.dofirstguess;
+    p.first_guess = args.dofirstguess; p.dosrsal = args.dosrsal;
 
     std::vector<float> cth, upix(n, 0.f), vpix(n, 0.f);
     int cx = 0, cy = 0;

@@ -734,7 +734,7 @@ void octane_params_default(octane_params* p)
     p->alpha = 5.; p->lambda = 1.; p->lambdac = 0.; p->scaleF = 0.5; p->scsig = 400.;   // src/main.cc:77-87
     p->kiters = 4; p->liters = 3; p->cgiters = 30; p->dozim = 1; p->setdevice = 0;
     p->pixuv = 0; p->dopolar = 0; p->domerc = 0; p->first_guess = 0; p->max_disp = 64;
-    p->doCTH = 0; p->ir = 0;
+    p->doCTH = 0; p->ir = 0; p->dosrsal = 0;
 }
 
 int octane_ctx_create(octane_ctx** out, int device)
@@ -890,13 +890,31 @@ int octane_pix2uv_band_dev(octane_ctx* c, const octane_nav* nav, double t1, doub
     return pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, row0, nrows, p, U, V, Ur, Vr);
 }
 
+namespace {
+constexpr int SRSAL_R = 18;    // radius of the -srsal window (src/oct_srsal_cuda.cu:78-79)
+int srsal_enqueue(octane_ctx* c, float* d_u, float* d_v, const float* d_cth, int nx, int ny, float* tmp_u, float* tmp_v);
+bool srsal_args_ok(const octane_params* p, const void* cth, int nx, int ny)
+{
+    if (!p->dosrsal) return true;
+    if (!cth) { set_err("dosrsal needs cth"); return false; }
+    if (nx <= SRSAL_R || ny <= SRSAL_R) { set_err("dosrsal needs a scene larger than 18 x 18"); return false; }
+    return true;
+}
+}  // namespace
+
 int octane_optical_flow_dev(octane_ctx* c, const float* d_img1, const float* d_img2, const float* d_cth, int nx, int ny, int nc,
                             const octane_nav* nav, double t1, double t2, const octane_params* p, float* d_u, float* d_v,
                             short* U, short* V, short* Ur, short* Vr, short* d_ctp)
 {
     if (!c || !d_img1 || !d_img2 || !nav || !p || !d_u || !d_v || !U || !V || !Ur || !Vr) { set_err("null argument"); return OCTANE_EINVAL; }
     if (p->doCTH && (!d_cth || !d_ctp)) { set_err("doCTH needs cth and ctp"); return OCTANE_EINVAL; }
+    if (!srsal_args_ok(p, d_cth, nx, ny)) return OCTANE_EINVAL;
     if (c->comm.world > 1) { set_err("context is banded: use the band entry points"); return OCTANE_EINVAL; }
+    const size_t fb = align_up((size_t)nx * ny * sizeof(float));
+    if (p->dosrsal) {
+        int rc = ensure_stage(c, 2 * fb);
+        if (rc) return rc;
+    }
     begin_call(c);
     int rc = solve_dev(c, d_img1, d_img2, nx, ny, nc, p, d_u, d_v);
     if (rc) return rc;
@@ -904,7 +922,10 @@ int octane_optical_flow_dev(octane_ctx* c, const float* d_img1, const float* d_i
         launch_ctp_pack(d_cth, d_ctp, (size_t)nx * ny, p->ir == 1, c->stream);
         c->launches++;
     }
-    return pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, 0, ny, p, U, V, Ur, Vr);
+    const int nrc = pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, 0, ny, p, U, V, Ur, Vr);
+    if (nrc < 0 || !p->dosrsal) return nrc;
+    rc = srsal_enqueue(c, d_u, d_v, d_cth, nx, ny, (float*)c->stage, (float*)(c->stage + fb));   // :100-105
+    return rc ? rc : nrc;
 }
 
 int octane_pix2uv(octane_ctx* c, const octane_nav* nav, double t1, double t2, const float* u, const float* v,
@@ -938,10 +959,11 @@ int octane_optical_flow(octane_ctx* c, const float* img1, const float* img2, con
 {
     if (!c || !img1 || !img2 || !nav || !p || !upix || !vpix || !U || !V || !Ur || !Vr) { set_err("null argument"); return OCTANE_EINVAL; }
     if (p->doCTH && (!cth || !ctp)) { set_err("doCTH needs cth and ctp"); return OCTANE_EINVAL; }
+    if (!srsal_args_ok(p, cth, nx, ny)) return OCTANE_EINVAL;
     if (c->comm.world > 1) { set_err("host-buffer entry points are single-GPU"); return OCTANE_EINVAL; }
     CUDA_OK(cudaSetDevice(c->device));
     const size_t n = (size_t)nx * ny, ib = n * nc * sizeof(float), fb = n * sizeof(float), sb = n * sizeof(short);
-    int rc = ensure_stage(c, 2 * ib + 3 * fb + 5 * sb);
+    int rc = ensure_stage(c, 2 * ib + 3 * fb + 5 * sb + (p->dosrsal ? 2 * fb + 256 : 0));
     if (rc) return rc;
     char* s = c->stage;
     float* d_i1 = (float*)s; s += ib;
@@ -959,8 +981,8 @@ int octane_optical_flow(octane_ctx* c, const float* img1, const float* img2, con
     }
     rc = solve_dev(c, d_i1, d_i2, nx, ny, nc, p, d_u, d_v);
     if (rc) return rc;
+    if (p->doCTH || p->dosrsal) CUDA_OK(cudaMemcpyAsync(d_cth, cth, fb, cudaMemcpyHostToDevice, c->stream));
     if (p->doCTH) {                            // src/oct_optical_flow.cc:71-88
-        CUDA_OK(cudaMemcpyAsync(d_cth, cth, fb, cudaMemcpyHostToDevice, c->stream));
         launch_ctp_pack(d_cth, d_s + 4 * n, n, p->ir == 1, c->stream);
         c->launches++;
         CUDA_OK(cudaMemcpyAsync(ctp, d_s + 4 * n, sb, cudaMemcpyDeviceToHost, c->stream));
@@ -971,6 +993,13 @@ int octane_optical_flow(octane_ctx* c, const float* img1, const float* img2, con
     CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_stage, 0));
     int nrc = pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, 0, ny, p, d_s, d_s + n, d_s + 2 * n, d_s + 3 * n);
     if (nrc < 0) { cudaStreamSynchronize(c->copy_stream); return nrc; }
+    if (p->dosrsal) {      // src/oct_optical_flow.cc:100-105: after the navigation, so only uPix / vPix are smoothed
+        float* tmp = (float*)(((uintptr_t)(d_s + 5 * n) + 255) & ~(uintptr_t)255);
+        rc = srsal_enqueue(c, d_u, d_v, d_cth, nx, ny, tmp, tmp + n);
+        if (rc) { cudaStreamSynchronize(c->copy_stream); return rc; }
+        CUDA_OK(cudaEventRecord(c->ev_stage, c->stream));
+        CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_stage, 0));
+    }
     CUDA_OK(cudaMemcpyAsync(upix, d_u, fb, cudaMemcpyDeviceToHost, c->copy_stream));
     CUDA_OK(cudaMemcpyAsync(vpix, d_v, fb, cudaMemcpyDeviceToHost, c->copy_stream));
     CUDA_OK(cudaMemcpyAsync(U, d_s, sb, cudaMemcpyDeviceToHost, c->stream));
@@ -1131,6 +1160,161 @@ int octane_zoom_in_float(octane_ctx* c, const float* in, int nx, int ny, float* 
     rc = octane_zoom_in_float_dev(c, d_in, nx, ny, d_out, nxx, nyy, interp);
     if (rc) return rc;
     CUDA_OK(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return OCTANE_OK;
+}
+
+// ---- oct_zoom_out_float (src/oct_zoom.cc:51-88): a finer field down to the image grid ----------
+int octane_zoom_out_size(int nx, int ny, double factor, int* nxx, int* nyy)
+{
+    if (!nxx || !nyy || nx <= 0 || ny <= 0 || !(factor > 0.0)) { set_err("null or invalid argument"); return OCTANE_EINVAL; }
+    *nxx = (int)((double)nx * factor + 0.5);       // oct_zoom_size, src/oct_zoom.cc:12-16
+    *nyy = (int)((double)ny * factor + 0.5);
+    return OCTANE_OK;
+}
+
+namespace {
+// Taps of oct_gaussian / oct_getGaussian_1D for this factor (src/oct_zoom.cc:64, src/oct_gaussian.cc:34-56),
+// evaluated on the host in double exactly as the reference does.  Returns 0 for the copy branch
+// (factor >= 0.999999, :74-81), 1 with taps filled, or a negative code.
+int zoom_out_taps(double factor, ZoomOutTaps* t)
+{
+    if (!(factor < 0.999999)) return 0;
+    const double sigma = 0.6 * sqrt(1.0 / (factor * factor) - 1.0);
+    int filtsize = 2 * sigma;                      // `(int) 2*sigma`: truncated on assignment
+    if (filtsize < 5) filtsize = 5;
+    if (filtsize > 32) { set_err("zoom-out factor below 1/27 is not supported (blur radius > 32)"); return OCTANE_EINVAL; }
+    const int wk = 2 * filtsize + 1;
+    const double s = 2.0 * sigma * sigma;
+    double sum = 0.0;
+    for (int x = -filtsize; x <= filtsize; x++) {
+        const double r = x;
+        t->gk[x + filtsize] = (exp(-(r * r) / s)) / (M_PI * s);
+        sum += t->gk[x + filtsize];
+    }
+    for (int i = 0; i < wk; ++i) t->gk[i] /= sum;
+    t->R = filtsize;
+    return 1;
+}
+
+int zoom_out_enqueue(octane_ctx* c, const float* d_in, int nx, int ny, float* d_out, int nxx, int nyy, double factor,
+                     int have_taps, const ZoomOutTaps& taps, double* tmp_a, double* tmp_b)
+{
+    c->launches += launch_zoom_out_float(d_in, nx, ny, d_out, nxx, nyy, factor, have_taps ? &taps : nullptr, tmp_a, tmp_b, c->stream);
+    CUDA_OK(cudaGetLastError());
+    return OCTANE_OK;
+}
+
+bool zoom_out_args_ok(int nx, int ny, double factor, int* nxx, int* nyy)
+{
+    if (nx <= 0 || ny <= 0 || !(factor > 0.0) || factor > 1.0) return false;
+    *nxx = (int)((double)nx * factor + 0.5);
+    *nyy = (int)((double)ny * factor + 0.5);
+    return *nxx > 0 && *nyy > 0 && *nxx <= nx && *nyy <= ny;
+}
+}  // namespace
+
+int octane_zoom_out_float_dev(octane_ctx* c, const float* d_in, int nx, int ny, float* d_out, double factor)
+{
+    int nxx, nyy;
+    if (!c || !d_in || !d_out || !zoom_out_args_ok(nx, ny, factor, &nxx, &nyy)) { set_err("null or invalid argument"); return OCTANE_EINVAL; }
+    ZoomOutTaps taps;
+    const int have = zoom_out_taps(factor, &taps);
+    if (have < 0) return have;
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t db = align_up((size_t)nx * ny * sizeof(double));
+    if (have) {
+        int rc = ensure_stage(c, 2 * db);
+        if (rc) return rc;
+    }
+    return zoom_out_enqueue(c, d_in, nx, ny, d_out, nxx, nyy, factor, have, taps, (double*)c->stage, (double*)(c->stage + db));
+}
+
+int octane_zoom_out_float(octane_ctx* c, const float* in, int nx, int ny, float* out, double factor)
+{
+    int nxx, nyy;
+    if (!c || !in || !out || !zoom_out_args_ok(nx, ny, factor, &nxx, &nyy)) { set_err("null or invalid argument"); return OCTANE_EINVAL; }
+    ZoomOutTaps taps;
+    const int have = zoom_out_taps(factor, &taps);
+    if (have < 0) return have;
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t db = align_up((size_t)nx * ny * sizeof(double)), ib = align_up((size_t)nx * ny * sizeof(float)),
+                 ob = (size_t)nxx * nyy * sizeof(float);
+    int rc = ensure_stage(c, 2 * db + ib + ob);
+    if (rc) return rc;
+    float* d_in = (float*)(c->stage + 2 * db);
+    float* d_out = (float*)(c->stage + 2 * db + ib);
+    begin_call(c);
+    CUDA_OK(cudaMemcpyAsync(d_in, in, (size_t)nx * ny * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    rc = zoom_out_enqueue(c, d_in, nx, ny, d_out, nxx, nyy, factor, have, taps, (double*)c->stage, (double*)(c->stage + db));
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return OCTANE_OK;
+}
+
+// ---- -srsal (oct_srsal_cu, src/oct_srsal_cuda.cu:73-147) ----------------------------------------
+namespace {
+void srsal_taps(SrsalTaps* t)
+{
+    const double sigpix = 20.;                      // :75-79
+    t->sigpix2 = -1. / (sigpix * sigpix * 2.);
+    const double filtsigma = 9;
+    const int filtsize = 2 * filtsigma;
+    const double s = 2.0 * filtsigma * filtsigma;   // oct_getGaussian_1D, src/oct_gaussian.cc:34-47
+    double sum = 0.0;
+    for (int x = -filtsize; x <= filtsize; x++) {
+        const double r = x;
+        t->gk[x + filtsize] = (exp(-(r * r) / s)) / (M_PI * s);
+        sum += t->gk[x + filtsize];
+    }
+    for (int i = 0; i < 2 * filtsize + 1; ++i) t->gk[i] /= sum;
+}
+
+// u, v -> tmp (filtered) -> back into u, v, all on the context's stream
+int srsal_enqueue(octane_ctx* c, float* d_u, float* d_v, const float* d_cth, int nx, int ny, float* tmp_u, float* tmp_v)
+{
+    SrsalTaps t;
+    srsal_taps(&t);
+    const size_t fb = (size_t)nx * ny * sizeof(float);
+    launch_srsal(d_u, d_v, d_cth, nx, ny, t, tmp_u, tmp_v, c->stream);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(d_u, tmp_u, fb, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_v, tmp_v, fb, cudaMemcpyDeviceToDevice, c->stream));
+    return OCTANE_OK;
+}
+}  // namespace
+
+int octane_srsal_dev(octane_ctx* c, float* d_u, float* d_v, const float* d_cth, int nx, int ny)
+{
+    // the reflected index stays inside the scene only for nx, ny > 18 (the reference reads out of bounds below that)
+    if (!c || !d_u || !d_v || !d_cth || nx <= SRSAL_R || ny <= SRSAL_R) { set_err("null or invalid argument"); return OCTANE_EINVAL; }
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t fb = align_up((size_t)nx * ny * sizeof(float));
+    int rc = ensure_stage(c, 2 * fb);
+    if (rc) return rc;
+    return srsal_enqueue(c, d_u, d_v, d_cth, nx, ny, (float*)c->stage, (float*)(c->stage + fb));
+}
+
+int octane_srsal(octane_ctx* c, float* u, float* v, const float* cth, int nx, int ny)
+{
+    if (!c || !u || !v || !cth || nx <= SRSAL_R || ny <= SRSAL_R) { set_err("null or invalid argument"); return OCTANE_EINVAL; }
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t fb = align_up((size_t)nx * ny * sizeof(float)), nb = (size_t)nx * ny * sizeof(float);
+    int rc = ensure_stage(c, 5 * fb);
+    if (rc) return rc;
+    float* d_u = (float*)(c->stage + 2 * fb);
+    float* d_v = (float*)(c->stage + 3 * fb);
+    float* d_c = (float*)(c->stage + 4 * fb);
+    begin_call(c);
+    CUDA_OK(cudaMemcpyAsync(d_u, u, nb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_v, v, nb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_c, cth, nb, cudaMemcpyHostToDevice, c->stream));
+    rc = srsal_enqueue(c, d_u, d_v, d_c, nx, ny, (float*)c->stage, (float*)(c->stage + fb));
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(u, d_u, nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(v, d_v, nb, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return OCTANE_OK;
 }

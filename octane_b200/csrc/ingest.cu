@@ -247,4 +247,79 @@ void launch_zoom_in_float(const float* in, int nx, int ny, float* out, int nxx, 
     k_zoom_in_float<<<grid, 256, 0, st>>>(in, nx, ny, out, nxx, nyy, interp);
 }
 
+// ---- down-scaling of a FINER ancillary field onto the image grid: oct_zoom_out_float,
+// src/oct_zoom.cc:51-88 = oct_gaussian (src/oct_gaussian.cc:48-104) on a double copy of the field, then
+// oct_bicubic (src/oct_bicubic.cc:36-97) at (ii / factor, jj / factor).  The reference does this on the
+// CPU in double; the three passes below keep its operation order and use the explicitly rounded
+// __dmul_rn / __dadd_rn so that nvcc cannot contract a product into the following sum: the outputs are
+// bit-identical to the reference's CPU object (x86-64, no FMA).  The taps come from the host (the
+// reference's exp() is glibc's).  Horizontal pass: 4 B read + 8 B written per input pixel; vertical pass
+// 8 + 8; sampling 16 taps per OUTPUT pixel (1 / factor^2 fewer than inputs).
+__device__ __forceinline__ double zcell_rn(double v0, double v1, double v2, double v3, double x)
+{
+    // v1 + 0.5*x*(v2 - v0 + x*(2.0*v0 - 5.0*v1 + 4.0*v2 - v3 + x*(3.0*(v1 - v2) + v3 - v0))), src/oct_bicubic.cc:10-18
+    const double t3 = __dsub_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn(v1, v2)), v3), v0);
+    const double t2 = __dadd_rn(__dsub_rn(__dadd_rn(__dsub_rn(__dmul_rn(2.0, v0), __dmul_rn(5.0, v1)), __dmul_rn(4.0, v2)), v3),
+                                __dmul_rn(x, t3));
+    const double t1 = __dadd_rn(__dsub_rn(v2, v0), __dmul_rn(x, t2));
+    return __dadd_rn(v1, __dmul_rn(__dmul_rn(0.5, x), t1));
+}
+
+template <typename TIn, bool VERT>
+__global__ void __launch_bounds__(256)
+k_zoomout_blur(const TIn* __restrict__ in, double* __restrict__ out, int nx, int ny, ZoomOutTaps t)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= nx || j >= ny) return;
+    double wsum = 0;
+    for (int k = -t.R; k < t.R; ++k) {              // the +R tap is dropped, src/oct_gaussian.cc:70,91
+        const size_t at = VERT ? (size_t)i + (size_t)nx * zbc(j + k, ny) : (size_t)zbc(i + k, nx) + (size_t)nx * j;
+        wsum = __dadd_rn(wsum, __dmul_rn(t.gk[k + t.R], (double)in[at]));
+    }
+    out[i + (size_t)nx * j] = wsum;
+}
+
+__global__ void __launch_bounds__(256)
+k_zoomout_sample(const double* __restrict__ Is, int nx, int ny, float* __restrict__ out, int nxx, int nyy, double factor)
+{
+    const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+    const int jj = blockIdx.y;
+    if (ii >= nxx || jj >= nyy) return;
+    const double uu = (double)ii / factor, vv = (double)jj / factor;
+    const int x = zbc((int)uu, nx), y = zbc((int)vv, ny);
+    const int cols[4] = { zbc((int)(uu - 1), nx), x, zbc((int)(uu + 1), nx), zbc((int)(uu + 2), nx) };
+    const size_t rows[4] = { (size_t)nx * zbc((int)(vv - 1), ny), (size_t)nx * y, (size_t)nx * zbc((int)(vv + 1), ny),
+                             (size_t)nx * zbc((int)(vv + 2), ny) };
+    const double fy = __dsub_rn(vv, (double)y), fx = __dsub_rn(uu, (double)x);
+    double v[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        v[c] = zcell_rn(Is[cols[c] + rows[0]], Is[cols[c] + rows[1]], Is[cols[c] + rows[2]], Is[cols[c] + rows[3]], fy);
+    out[ii + (size_t)nxx * jj] = (float)zcell_rn(v[0], v[1], v[2], v[3], fx);
+}
+
+__global__ void __launch_bounds__(256)
+k_zoomout_copy(const float* __restrict__ in, float* __restrict__ out, size_t n)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = in[k];
+}
+
+int launch_zoom_out_float(const float* in, int nx, int ny, float* out, int nxx, int nyy, double factor,
+                          const ZoomOutTaps* taps, double* tmp_a, double* tmp_b, cudaStream_t st)
+{
+    if (!taps) {       // factor >= 0.999999: in[ii + nxx*jj] -> out[ii + nxx*jj], src/oct_zoom.cc:79-81
+        const size_t n = (size_t)nxx * nyy;
+        k_zoomout_copy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+        return 1;
+    }
+    dim3 grid((nx + 255) / 256, ny);
+    k_zoomout_blur<float, false><<<grid, 256, 0, st>>>(in, tmp_a, nx, ny, *taps);
+    k_zoomout_blur<double, true><<<grid, 256, 0, st>>>(tmp_a, tmp_b, nx, ny, *taps);
+    dim3 grid2((nxx + 255) / 256, nyy);
+    k_zoomout_sample<<<grid2, 256, 0, st>>>(tmp_b, nx, ny, out, nxx, nyy, factor);
+    return 3;
+}
+
 }  // namespace octane

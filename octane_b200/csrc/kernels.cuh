@@ -113,7 +113,24 @@ void launch_navcal_grid(int grid_kind, const float* data2, const short* x, const
                         float xOffset, float yScale, float yOffset, float R, float lon0_rad, float lat1_rad, int donav,
                         float* data3, float* lat, float* lon, cudaStream_t st);
 void launch_zoom_in_float(const float* in, int nx, int ny, float* out, int nxx, int nyy, int interp, cudaStream_t st);
+// oct_zoom_out_float: taps == nullptr selects the copy branch (factor >= 0.999999); returns the number of launches
+struct ZoomOutTaps {
+    int R;
+    double gk[2 * 32 + 1];
+};
+int launch_zoom_out_float(const float* in, int nx, int ny, float* out, int nxx, int nyy, double factor,
+                          const ZoomOutTaps* taps, double* tmp_a, double* tmp_b, cudaStream_t st);
 void launch_uv2pix(float* u, float* v, const float* lat, const float* lon, const short* xs, const short* ys, int nx,
                    int ny, const Uv2PixParams& q, cudaStream_t st);
+
+
+// ---- post.cu
+// -srsal: 37 x 37 bilateral filter of the pixel displacements, weights from the cloud-top heights
+struct SrsalTaps {
+    double gk[37];
+    double sigpix2;
+};
+void launch_srsal(const float* u, const float* v, const float* cth, int nx, int ny, const SrsalTaps& t,
+                  float* u_out, float* v_out, cudaStream_t st);
 
 }  // namespace octane

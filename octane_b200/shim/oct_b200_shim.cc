@@ -14,6 +14,11 @@
 //        replaces src/oct_navcal_cuda.cu:100 (ingest: calibration, normalisation, lat/lon)
 //   void oct_uv2pix(GOESVar&, float*, float*, double, OFFlags)
 //        replaces src/oct_pix2uv_cuda.cu:372 (first-guess winds -> pixel displacements)
+//   void oct_srsal_cu(float*, float*, float*, int, int, OFFlags)
+//        replaces src/oct_srsal_cuda.cu:73 (-srsal post-smoother)
+//   void oct_zoom_in_float(float*, float*, int, int, int, int, int, int)
+//   void oct_zoom_out_float(float*, float*, int, int, double, int, int)
+//        replace src/oct_zoom.cc:180 and :51 (regridding of heights / extra channels; CPU code in the reference)
 //
 // on top of the C ABI in include/octane_b200.h, so that a maintainer drops the
 // two .cu objects from the reference's link line, adds this file and
@@ -197,4 +202,31 @@ void oct_merc_navcal_cuda(float* data2, short* data2s, short* x, short* y, short
 {
     grid_navcal(2, data2, data2s, x, y, xs, ys, nx, ny, data3, lat, lon, xScale, xOffset, yScale, yOffset, lon0, 0.f, R, donav, 0,
                 args);
+}
+
+// -srsal post-smoother, called by the dispatcher after the navigation (src/oct_optical_flow.cc:100-105);
+// replaces src/oct_srsal_cuda.cu:73.  In place on upix / vpix.
+void oct_srsal_cu(float* upix, float* vpix, float* CTHsub21, int nx, int ny, OFFlags args)
+{
+    octane_ctx* c = context_for(args.setdevice);
+    if (octane_srsal(c, upix, vpix, CTHsub21, nx, ny) < 0) die("oct_srsal_cu");
+}
+
+// Regridding of cloud-top heights / extra channels onto the image grid, CPU code in the reference
+// (src/oct_zoom.cc:180 and :51, called by the readers: src/oct_fileread.cc:370,379,796,805).  A maintainer
+// who wants them on the GPU removes (or weakens with objcopy, as the drop-in test build does) the two
+// definitions in oct_zoom.cc.  Neither function gets OFFlags: device 0.
+void oct_zoom_in_float(float* flow, float* flowout, int nx, int ny, int nxx, int nyy, int cnum, int interp)
+{
+    octane_ctx* c = context_for(0);
+    const long cnumt = (long)cnum * ((long)nxx * nyy);                        // plane offset, :190
+    if (octane_zoom_in_float(c, flow, nx, ny, flowout + cnumt, nxx, nyy, interp) < 0) die("oct_zoom_in_float");
+}
+
+void oct_zoom_out_float(float* image, float* imageout, int nx, int ny, double factor, int verb, int cnum)
+{
+    if (verb == 1) exit(0);                                                   // :61
+    octane_ctx* c = context_for(0);
+    // the reference stores pixel k at imageout[k + cnum] -- an ELEMENT offset (:84), kept as it is
+    if (octane_zoom_out_float(c, image, nx, ny, imageout + cnum, factor) < 0) die("oct_zoom_out_float");
 }

@@ -31,6 +31,10 @@
 #include <string.h>
 #include <stdint.h>
 
+#ifndef M_PI            /* -std=c99 hides it; the value is glibc's */
+#define M_PI 3.14159265358979323846
+#endif
+
 typedef struct {
     double alpha, lambda, lambdac, scaleF;
     int kiters, liters, cgiters, dozim;
@@ -864,5 +868,140 @@ int oracle_navcal_grid(int grid, const float *data2, const short *x, const short
             if (lat && lon) { lat[k] = la; lon[k] = lo; }
             data3[k] = data2[k];
         }
+    return 0;
+}
+
+/* ---- down-scaling of a finer ancillary field onto the image grid: oct_zoom_out_float,
+ * src/oct_zoom.cc:51-88, with oct_gaussian / oct_getGaussian_1D (src/oct_gaussian.cc:34-104) and
+ * oct_bicubic (src/oct_bicubic.cc:36-97).  All arithmetic in double on a double copy of the field;
+ * the blur drops the +R tap like the solver's (kk < filtsize, :70,91) and its radius is
+ * (int)(2 sigma), at least 5 (:54-56).  out is the dense nxx x nyy plane (the reference writes it at
+ * imageout + cnum, :84 -- an element offset, not a plane offset; the caller places the plane). */
+void oracle_zoom_out_size(int nx, int ny, double factor, int *nxx, int *nyy)
+{
+    *nxx = (int)((double)nx * factor + 0.5);       /* src/oct_zoom.cc:12-16 */
+    *nyy = (int)((double)ny * factor + 0.5);
+}
+
+int oracle_gaussian_taps(double sigma, double *GK, int max_taps)
+{
+    int filtsize = 2 * sigma;                      /* (int) 2*sigma: the product is truncated on assignment */
+    if (filtsize < 5) filtsize = 5;
+    const int wk = 2 * filtsize + 1;
+    if (wk > max_taps) return -1;
+    const double s = 2.0 * sigma * sigma;
+    double sum = 0.0;
+    for (int x = -filtsize; x <= filtsize; x++) {
+        const double r = x;
+        GK[x + filtsize] = (exp(-(r * r) / s)) / (M_PI * s);
+        sum += GK[x + filtsize];
+    }
+    for (int i = 0; i < wk; ++i) GK[i] /= sum;
+    return filtsize;
+}
+
+static double zbicubic_d(const double *in, double uu, double vv, int nx, int ny)
+{
+    const int x = zbc((int)uu, nx), y = zbc((int)vv, ny);
+    const int cols[4] = { zbc((int)(uu - 1), nx), x, zbc((int)(uu + 1), nx), zbc((int)(uu + 2), nx) };
+    const int rows[4] = { zbc((int)(vv - 1), ny), y, zbc((int)(vv + 1), ny), zbc((int)(vv + 2), ny) };
+    double v[4];
+    /* pol[c][r] = input[cols[c] + nx rows[r]]; oct_bicubic_cell(pol, uu - x, vv - y) runs oct_cell over r
+     * with its second argument (vv - y), then over c with (uu - x) */
+    for (int c = 0; c < 4; c++) {
+        double p[4];
+        for (int r = 0; r < 4; r++) p[r] = in[cols[c] + (size_t)nx * rows[r]];
+        v[c] = zcell(p, vv - y);
+    }
+    return zcell(v, uu - x);
+}
+
+int oracle_zoom_out_float(const float *in, int nx, int ny, float *out, double factor)
+{
+    int nxx, nyy;
+    oracle_zoom_out_size(nx, ny, factor, &nxx, &nyy);
+    if (!(factor < 0.999999)) {                    /* :74-81: plain copy, read with the OUTPUT stride */
+        for (int jj = 0; jj < nyy; jj++)
+            for (int ii = 0; ii < nxx; ii++) out[ii + (size_t)nxx * jj] = in[ii + (size_t)nxx * jj];
+        return 0;
+    }
+    const size_t n = (size_t)nx * ny;
+    double *Is = (double *)malloc(n * sizeof(double)), *tmp = (double *)malloc(n * sizeof(double));
+    double GK[257];
+    const double sigma = 0.6 * sqrt(1.0 / (factor * factor) - 1.0);
+    const int R = oracle_gaussian_taps(sigma, GK, 257);
+    if (!Is || !tmp || R < 0) { free(Is); free(tmp); return -1; }
+    for (size_t i = 0; i < n; i++) Is[i] = in[i];
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) {
+            double wsum = 0;
+            for (int k = -R; k < R; ++k) wsum = wsum + GK[k + R] * Is[zbc(i + k, nx) + (size_t)nx * j];
+            tmp[i + (size_t)nx * j] = wsum;
+        }
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) {
+            double wsum = 0;
+            for (int l = -R; l < R; ++l) wsum = wsum + GK[l + R] * tmp[i + (size_t)nx * zbc(j + l, ny)];
+            Is[i + (size_t)nx * j] = wsum;
+        }
+#pragma omp parallel for schedule(static)
+    for (int jj = 0; jj < nyy; jj++)
+        for (int ii = 0; ii < nxx; ii++) {
+            const double i2 = (double)ii / factor, j2 = (double)jj / factor;
+            out[ii + (size_t)nxx * jj] = zbicubic_d(Is, i2, j2, nx, ny);
+        }
+    free(Is); free(tmp);
+    return 0;
+}
+
+/* ---- the optional post-smoother of the pixel displacements (-srsal): octsrsalcuda + oct_srsal_cu,
+ * src/oct_srsal_cuda.cu:16-71,73-147.  37 x 37 bilateral filter: spatial Gaussian (sigma 9 px, radius 18,
+ * normalised 1-D taps) times a range weight exp(-(dCTH)^2 / (2 * 20^2)) on the cloud-top heights; double
+ * accumulators, kc (x offset) outer and lc (y offset) inner; the reflecting index rule of oct_bc_cuda
+ * (:16-28: -x below, 2 nx - x - 1 above).  The device code contracts `au += u * a1` into an fma (nvcc
+ * default), restated here with fma().  u, v are filtered in place (from a copy). */
+int oracle_srsal(float *u, float *v, const float *cth, int nx, int ny)
+{
+    const double sigpix = 20., sigpix2 = -1. / (sigpix * sigpix * 2.);
+    const double filtsigma = 9;
+    const int filtsize = 2 * filtsigma;
+    double GK[37];
+    if (nx <= filtsize || ny <= filtsize) return -1;      /* the reflected index would leave the array */
+    {
+        const double s = 2.0 * filtsigma * filtsigma;
+        double sum = 0.0;
+        for (int x = -filtsize; x <= filtsize; x++) { const double r = x; GK[x + filtsize] = (exp(-(r * r) / s)) / (M_PI * s); sum += GK[x + filtsize]; }
+        for (int i = 0; i < 2 * filtsize + 1; ++i) GK[i] /= sum;
+    }
+    const size_t n = (size_t)nx * ny;
+    float *u0 = (float *)malloc(n * sizeof(float)), *v0 = (float *)malloc(n * sizeof(float));
+    if (!u0 || !v0) { free(u0); free(v0); return -1; }
+    memcpy(u0, u, n * sizeof(float)); memcpy(v0, v, n * sizeof(float));
+#pragma omp parallel for schedule(static)
+    for (int jc = 0; jc < ny; jc++)
+        for (int ic = 0; ic < nx; ic++) {
+            const float pixc = cth[ic + (size_t)nx * jc];
+            double au = 0, av = 0, a2 = 0;
+            for (int kc = 0; kc < 2 * filtsize + 1; kc++)
+                for (int lc = 0; lc < 2 * filtsize + 1; lc++) {
+                    int ivc = ic + kc - filtsize, jvc = jc + lc - filtsize;
+                    if (ivc < 0) ivc = 0 - ivc;
+                    if (ivc >= nx) ivc = nx - (ivc - nx + 1);
+                    if (jvc < 0) jvc = 0 - jvc;
+                    if (jvc >= ny) jvc = ny - (jvc - ny + 1);
+                    const size_t l2 = ivc + (size_t)jvc * nx;
+                    const float pixl = cth[l2];
+                    const double pixm = pixl - pixc;            /* float subtraction, then widened (:57) */
+                    const double a1 = GK[kc] * GK[lc] * exp((pixm) * (pixm)*sigpix2);
+                    a2 += a1;
+                    au = fma((double)u0[l2], a1, au);
+                    av = fma((double)v0[l2], a1, av);
+                }
+            u[ic + (size_t)nx * jc] = (au / a2);
+            v[ic + (size_t)nx * jc] = (av / a2);
+        }
+    free(u0); free(v0);
     return 0;
 }

@@ -223,15 +223,73 @@ def zoom_in_float(field, nxx, nyy, interp=1):
     return out
 
 
-def ref_zoom_in_float(field, nxx, nyy, interp=1):
-    """the reference's own CPU function (oracle/_ref/libref_cpu.so; no GPU needed)"""
+def ref_zoom_in_float(field, nxx, nyy, interp=1, L=None):
+    """the reference's own CPU function (oracle/_ref/libref_cpu.so; no GPU needed); L = ref_shim(): the shim's
+    definition under the same signature"""
     field = np.ascontiguousarray(field, np.float32)
     ny, nx = field.shape
-    L = ref_cpu()
+    L = L or ref_cpu()
     L.ref_zoom_in_float.argtypes = [_f32, _f32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     out = np.zeros((nyy, nxx), np.float32)
     L.ref_zoom_in_float(field, out, nx, ny, nxx, nyy, interp)
     return out
+
+
+def zoom_out_size(nx, ny, factor):
+    L = lib()
+    L.oracle_zoom_out_size.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    a, b = C.c_int(), C.c_int()
+    L.oracle_zoom_out_size(nx, ny, factor, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def zoom_out_float(field, factor):
+    """oct_zoom_out_float restated (src/oct_zoom.cc:51-88): blur in double, bicubic sample at ii / factor"""
+    field = np.ascontiguousarray(field, np.float32)
+    ny, nx = field.shape
+    nxx, nyy = zoom_out_size(nx, ny, factor)
+    L = lib()
+    L.oracle_zoom_out_float.argtypes = [_f32, C.c_int, C.c_int, _f32, C.c_double]
+    out = np.zeros((nyy, nxx), np.float32)
+    assert L.oracle_zoom_out_float(field, nx, ny, out, factor) == 0
+    return out
+
+
+def ref_zoom_out_float(field, factor, cnum=0, L=None):
+    """the reference's own CPU function (oracle/_ref/libref_cpu.so); returns the raw output buffer of
+    nxx*nyy + cnum floats (the plane starts at element cnum) reshaped when cnum == 0.  L = ref_shim(): the
+    shim's definition under the same signature"""
+    field = np.ascontiguousarray(field, np.float32)
+    ny, nx = field.shape
+    nxx, nyy = zoom_out_size(nx, ny, factor)
+    L = L or ref_cpu()
+    L.ref_zoom_out_float.argtypes = [_f32, _f32, C.c_int, C.c_int, C.c_double, C.c_int]
+    out = np.zeros(nxx * nyy + cnum, np.float32)
+    L.ref_zoom_out_float(field, out, nx, ny, factor, cnum)
+    return out.reshape(nyy, nxx) if cnum == 0 else out
+
+
+def srsal(u, v, cth):
+    """-srsal bilateral post-smoother restated (src/oct_srsal_cuda.cu:35-71)"""
+    u = np.array(u, np.float32, order="C"); v = np.array(v, np.float32, order="C")
+    cth = np.ascontiguousarray(cth, np.float32)
+    ny, nx = u.shape
+    L = lib()
+    L.oracle_srsal.argtypes = [_f32, _f32, _f32, C.c_int, C.c_int]
+    assert L.oracle_srsal(u, v, cth, nx, ny) == 0
+    return u, v
+
+
+def ref_srsal(u, v, cth, L=None):
+    """the reference's oct_srsal_cu (needs a GPU)"""
+    L = L or ref_cuda()
+    u = np.array(u, np.float32, order="C"); v = np.array(v, np.float32, order="C")
+    cth = np.ascontiguousarray(cth, np.float32)
+    ny, nx = u.shape
+    L.ref_srsal.argtypes = [_f32, _f32, _f32, C.c_int, C.c_int, C.POINTER(RefParams)]
+    rp = ref_params()
+    L.ref_srsal(u, v, cth, nx, ny, C.byref(rp))
+    return u, v
 
 
 # ---- the reference itself -------------------------------------------------

@@ -14,6 +14,8 @@
 //   oct_zoom_out / oct_zoom_in     src/oct_zoom.cc:17,154
 //   oct_navcal_cuda                src/oct_navcal_cuda.cu:100
 //   oct_uv2pix                     src/oct_pix2uv_cuda.cu:372
+//   oct_zoom_in_float / oct_zoom_out_float   src/oct_zoom.cc:180,51
+//   oct_srsal_cu                   src/oct_srsal_cuda.cu:73
 // Only tests/, __graft_entry__.smoke() and bench.py's baseline legs load it.
 #include <cstring>
 #include <string>
@@ -25,11 +27,13 @@ void oct_patch_match_optical_flow(float*, float*, float*, float*, int, int, OFFl
 void oct_zoom_out(double*, double*, int, int, double, int);
 void oct_zoom_in(double*, double*, int, int, int, int);
 void oct_zoom_in_float(float*, float*, int, int, int, int, int, int);
+void oct_zoom_out_float(float*, float*, int, int, double, int, int);
 #ifdef REF_WITH_CUDA
 void oct_variational_optical_flow(Image, Image, float*, float*, float*, int, int, int, OFFlags);
 void oct_pix2uv_cuda(GOESVar&, double, float*, float*, short*, short*, short*, short*, OFFlags);
 int oct_optical_flow(GOESVar&, GOESVar&, OFFlags&);
 void oct_uv2pix(GOESVar&, float*, float*, double, OFFlags);
+void oct_srsal_cu(float*, float*, float*, int, int, OFFlags);
 void oct_polar_navcal_cuda(float*, short*, short*, short*, short*, short*, int, int, int, int, int, int, float*, float*, float*,
                            float, float, float, float, float, float, float, int, int, OFFlags);
 void oct_merc_navcal_cuda(float*, short*, short*, short*, short*, short*, int, int, int, int, int, int, float*, float*, float*,
@@ -98,6 +102,13 @@ int ref_zoom_out(const double* in, double* out, int nx, int ny, double factor)
 int ref_zoom_in_float(const float* in, float* out, int nx, int ny, int nxx, int nyy, int interp)
 {
     oct_zoom_in_float(const_cast<float*>(in), out, nx, ny, nxx, nyy, 0, interp);      // src/oct_zoom.cc:180
+    return 0;
+}
+
+// out must hold nxx*nyy + cnum floats: the reference stores pixel k at out[k + cnum] (src/oct_zoom.cc:84)
+int ref_zoom_out_float(const float* in, float* out, int nx, int ny, double factor, int cnum)
+{
+    oct_zoom_out_float(const_cast<float*>(in), out, nx, ny, factor, 0, cnum);            // src/oct_zoom.cc:51
     return 0;
 }
 
@@ -221,6 +232,14 @@ int ref_uv2pix(const RefNav* nav, double t1, double t2, const float* lat, const 
     g.latVal = const_cast<float*>(lat); g.lonVal = const_cast<float*>(lon);
     g.x = const_cast<short*>(x); g.y = const_cast<short*>(y);
     oct_uv2pix(g, u, v, t2, a);
+    return 0;
+}
+
+// -srsal post-smoother, in place on u, v (src/oct_srsal_cuda.cu:73)
+int ref_srsal(float* u, float* v, const float* cth, int nx, int ny, const RefParams* p)
+{
+    OFFlags a; defaults(a, p);
+    oct_srsal_cu(u, v, const_cast<float*>(cth), nx, ny, a);
     return 0;
 }
 #endif

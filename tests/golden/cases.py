@@ -166,3 +166,52 @@ def gridnav_inputs(c):
     y, x = np.mgrid[0:ny, 0:nx].astype(np.float32)
     data = (120.0 + 90.0 * np.sin(x / 7.0) * np.cos(y / 5.0)).astype(np.float32)
     return data, np.arange(nx, dtype=np.int16), np.arange(ny, dtype=np.int16)
+
+
+# ---- regridding of a finer field (oct_zoom_out_float) and the -srsal post-smoother (oct_srsal_cu) ---
+# (ny, nx), factor: integer ratios (the GOES channel pairs: 0.5 km -> 1 km / 2 km), non-integer ratios
+# (bicubic between blurred pixels), a blur radius above the minimum of 5 (factor 1/8 -> 9), the copy branch
+ZOOMOUT = {
+    "half": ((97, 131), 0.5),
+    "quarter": ((120, 160), 0.25),
+    "third": ((90, 77), 1.0 / 3.0),
+    "ragged": ((64, 80), 0.37),
+    "eighth": ((200, 240), 0.125),
+    "copy": ((50, 50), 1.0),
+    "almost_one": ((40, 40), 0.9999995),
+    "tiny": ((7, 9), 0.5),
+}
+
+
+def zoomout_input(name):
+    (ny, nx), factor = ZOOMOUT[name]
+    rng = np.random.default_rng(nx * 7 + ny)
+    return (rng.standard_normal((ny, nx)) * 1000 + 5000).astype(np.float32), factor
+
+
+SRSAL = {
+    # cloud deck with sharp edges (range weight switches neighbours off) and smooth height variation
+    "srsal_96x80_deck": dict(nx=96, ny=80, seed=31, kind="deck"),
+    # barely larger than the window radius: every pixel reflects on both sides
+    "srsal_23x19_small": dict(nx=23, ny=19, seed=32, kind="smooth"),
+    # constant heights: the range weight is 1 and the filter is the plain truncated Gaussian
+    "srsal_70x50_flat": dict(nx=70, ny=50, seed=33, kind="flat"),
+}
+
+
+def srsal_inputs(c):
+    nx, ny = c["nx"], c["ny"]
+    rng = np.random.default_rng(c["seed"])
+    y, x = np.mgrid[0:ny, 0:nx].astype(np.float32)
+    u = (1.7 * np.sin(x / 17.0) + 0.9 * np.cos(y / 13.0) + 0.4 + 0.3 * rng.standard_normal((ny, nx))).astype(np.float32)
+    v = (-1.1 * np.cos(x / 11.0) * np.sin(y / 19.0) - 0.25 + 0.3 * rng.standard_normal((ny, nx))).astype(np.float32)
+    if c["kind"] == "flat":
+        cth = np.full((ny, nx), 8000.0, np.float32)
+    elif c["kind"] == "smooth":
+        cth = (6000.0 + 30.0 * np.sin(x / 5.0) * np.cos(y / 4.0)).astype(np.float32)
+    else:
+        cth = (2000.0 + 15.0 * np.sin(x / 9.0) + 10.0 * np.cos(y / 7.0)).astype(np.float32)
+        cth[(x - 0.55 * nx) ** 2 + (y - 0.45 * ny) ** 2 < (0.28 * ny) ** 2] += 9000.0      # a tower
+        cth[:, : nx // 5] += 40.0                                                          # a low step (partial weight)
+        cth += (5.0 * rng.standard_normal((ny, nx))).astype(np.float32)
+    return u, v, cth

@@ -52,10 +52,21 @@ def ingest(out):
         print(name, "upix range", float(np.nanmin(up)), float(np.nanmax(up)), "zeros", int((up == 0).sum()), flush=True)
 
 
+def srsal(out):
+    """fixtures of the -srsal post-smoother (the reference's oct_srsal_cu, a CUDA kernel)"""
+    for name, c in cases.SRSAL.items():
+        u, v, cth = cases.srsal_inputs(c)
+        us, vs = O.ref_srsal(u, v, cth)
+        np.savez_compressed(os.path.join(out, name + ".npz"), u=us, v=vs)
+        print(name, "u range", float(us.min()), float(us.max()), "mean |du|", float(np.abs(us - u).mean()), flush=True)
+
+
 def main(out):
     os.makedirs(out, exist_ok=True)
     if "--ingest-only" in sys.argv:
         return ingest(out)
+    if "--srsal-only" in sys.argv:
+        return srsal(out)
     for name, c in cases.VARIATIONAL.items():
         img1, img2, u0, v0 = cases.variational_inputs(c)
         kw = dict(c.get("params", {}))
@@ -101,6 +112,7 @@ def main(out):
                             dT=np.float32(dT.value))
         print("dispatch ir", ir, "CTP range", int(outs[4].min()), int(outs[4].max()), flush=True)
     ingest(out)
+    srsal(out)
 
 
 if __name__ == "__main__":

@@ -126,10 +126,13 @@ def test_reader_rejects_what_it_cannot_read(tmp_path):
     G.write_plane_file(os.path.join(tmp, "cth_small.nc"), Cloud_Top_Height_Effective=np.zeros((10, 12), np.float32))
     r = run("-i1", d["f1"], "-i2", d["f2"], "-i1cth", os.path.join(tmp, "cth_small.nc"), "-dry_run", check=False)
     assert r.returncode == 1 and "regridding" in r.stderr
+    r = run("-i1", d["f1"], "-i2", d["f2"], "-srsal", "-dry_run", check=False)       # the smoother's range weight needs heights
+    assert r.returncode == 1 and "-srsal needs cloud-top heights" in r.stderr
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["default", "pd_cth", "firstguess", "cth_coarse_nn", "two_channels"])
+@pytest.mark.parametrize("mode", ["default", "pd_cth", "firstguess", "cth_coarse_nn", "two_channels", "cth_fine_srsal",
+                                  "channel2_fine"])
 def test_cli_end_to_end_matches_the_library(tmp_path, ctx, mode):
     """file -> octane -> outfile.nc equals ingest + flow + navigation called through the C ABI"""
     from scipy.io import netcdf_file
@@ -160,6 +163,25 @@ def test_cli_end_to_end_matches_the_library(tmp_path, ctx, mode):
         args += ["-i1cth", os.path.join(tmp, "cth4.nc"), "-nncth", "-ir"]
         p = ob.default_params(doCTH=1, ir=1)
         cth = ctx.oct_zoom_in_float(small, nx, ny, 0)
+    if mode == "cth_fine_srsal":      # CTH on a 2x finer grid (oct_zoom_out_float), -srsal smoothing of Upix / Vpix
+        yy, xx = np.mgrid[0:2 * ny, 0:2 * nx].astype(np.float32)
+        fine = (6000 + 50 * np.cos(xx / 23.0) * np.sin(yy / 17.0) + 3000 * (xx > nx)).astype(np.float32)
+        G.write_plane_file(os.path.join(tmp, "cth_fine.nc"), Cloud_Top_Height_Effective=fine)
+        args += ["-pd", "-i1cth", os.path.join(tmp, "cth_fine.nc"), "-srsal"]
+        p = ob.default_params(pixuv=1, doCTH=1, dosrsal=1)
+        cth = ctx.oct_zoom_out_float(fine, 0.5)
+        assert cth.shape == (ny, nx)
+    if mode == "channel2_fine":       # -ic21 / -ic22: a second channel on a 2x finer grid, blurred and decimated
+        d2 = _pair_files(os.path.join(tmp), nx=320, ny=256, band=2, seed=34, prefix="c2f_")
+        args += ["-ic21", d2["f1"], "-ic22", d2["f2"]]
+        cal2 = ob.goes_cal(d2["radScale"], d2["radOffset"], band=2, fk1=202263.0, fk2=3698.19, bc1=0.43361, bc2=0.99939,
+                           kap1=0.0019486)
+        a2, _, _ = ctx.oct_navcal_cuda(d2["r1"], d2["xc"], d2["yc"], nav, cal2)
+        cal2.donav = 0
+        b2, _, _ = ctx.oct_navcal_cuda(d2["r2"], d2["xc"], d2["yc"], nav, cal2)
+        img1 = np.ascontiguousarray(np.stack([img1, ctx.oct_zoom_out_float(a2, 0.5)]))
+        img2 = np.ascontiguousarray(np.stack([img2, ctx.oct_zoom_out_float(b2, 0.5)]))
+        nc = 2
     if mode == "two_channels":        # -ic21 / -ic22: a second channel on the same grid
         d2 = _pair_files(os.path.join(tmp), nx=160, ny=128, band=13, seed=33, prefix="c2_")
         args += ["-ic21", d2["f1"], "-ic22", d2["f2"]]
@@ -188,6 +210,13 @@ def test_cli_end_to_end_matches_the_library(tmp_path, ctx, mode):
         assert np.array_equal(v["CTP"][:], want["CTP"]) and int(v["optical_flow_settings"].K_Iterations) == 3
     if mode == "cth_coarse_nn":
         assert np.array_equal(v["CTP"][:], want["CTP"]) and float(v["CTP"].interpcth) == 0.0
+    if mode == "cth_fine_srsal":
+        assert np.array_equal(v["Upix"][:], want["uPix"]) and np.array_equal(v["Vpix"][:], want["vPix"])
+        assert np.array_equal(v["CTP"][:], want["CTP"])
+        raw = v["U_raw"][:].astype(np.float32) / 100.0          # the shorts come from the UNSMOOTHED flow
+        assert np.abs(want["uPix"] - raw).max() > 0.02
+    if mode == "channel2_fine":
+        assert "Rad2" not in v                                   # written only for channels on channel 1's grid
     if mode == "two_channels":
         assert np.array_equal(v["Rad2"][:], d2["r1"]) and "planck_fk1_2" in v and "Rad3" not in v
     assert int(v["optical_flow_settings"].dofirstguess) == int(mode == "firstguess")
