@@ -275,6 +275,13 @@ int octane_comm_rank(octane_ctx* ctx, int* rank, int* world);
 int octane_variational_flow_band_dev(octane_ctx* ctx, const float* d_img1_band, const float* d_img2_band,
                                      int nx, int ny, int nc, const octane_params* p,
                                      float* d_u_band_inout, float* d_v_band_inout);
+/* The same with a first guess (p->first_guess = 1, optionally p->lambdac): d_fg_u / d_fg_v hold rows [in0,in1) of the
+ * first-guess displacement field (band + overlap, like the images: the hint field of every level is blurred and
+ * decimated from them locally, nothing is exchanged); d_u / d_v receive rows [own0,own1) of the flow. */
+int octane_variational_flow_band_fg_dev(octane_ctx* ctx, const float* d_img1_band, const float* d_img2_band,
+                                        const float* d_fg_u_band, const float* d_fg_v_band,
+                                        int nx, int ny, int nc, const octane_params* p,
+                                        float* d_u_band_out, float* d_v_band_out);
 /* rows [row0,row0+nrows) of an nx-wide scene; d_u etc. hold just those rows */
 int octane_pix2uv_band_dev(octane_ctx* ctx, const octane_nav* nav, double t1, double t2,
                            const float* d_u, const float* d_v, int nx, int row0, int nrows,

@@ -68,7 +68,7 @@ EXPORTS = [
     "octane_stage_blur_decimate", "octane_stage_gradient", "octane_stage_zoom_in",
     "octane_stage_build", "octane_stage_pcg",
     "octane_band_plan", "octane_comm_unique_id", "octane_comm_init", "octane_comm_rank",
-    "octane_variational_flow_band_dev", "octane_pix2uv_band_dev",
+    "octane_variational_flow_band_dev", "octane_variational_flow_band_fg_dev", "octane_pix2uv_band_dev",
 ]
 
 _lib = None
@@ -132,6 +132,7 @@ def load() -> C.CDLL:
     L.octane_comm_init.argtypes = [vp, C.c_char_p, i, i]
     L.octane_comm_rank.argtypes = [vp, ip, ip]
     L.octane_variational_flow_band_dev.argtypes = [vp, vp, vp, i, i, i, PP, vp, vp]
+    L.octane_variational_flow_band_fg_dev.argtypes = [vp, vp, vp, vp, vp, i, i, i, PP, vp, vp]
     L.octane_pix2uv_band_dev.argtypes = [vp, NP, d, d, vp, vp, i, i, i, PP, vp, vp, vp, vp]
     _lib = L
     return L

@@ -212,10 +212,18 @@ class Context:
             self._before_torch()
         return u, v
 
-    def oct_variational_optical_flow_band(self, geo1_band, geo2_band, u_band, v_band, nx, ny, p: Params, nc: int = 1):
+    def oct_variational_optical_flow_band(self, geo1_band, geo2_band, u_band, v_band, nx, ny, p: Params, nc: int = 1,
+                                          fg_u_band=None, fg_v_band=None):
+        """row-band solve (collective).  geo*_band and the optional first guess fg_*_band hold rows [in0,in1) of
+        band_plan(); u_band / v_band receive rows [own0,own1)."""
         self._after_torch()
-        self._check(self._L.octane_variational_flow_band_dev(self._h, _ptr(geo1_band), _ptr(geo2_band), nx, ny, nc,
-                                                             C.byref(p), _ptr(u_band), _ptr(v_band)))
+        if p.first_guess and fg_u_band is not None:
+            self._check(self._L.octane_variational_flow_band_fg_dev(self._h, _ptr(geo1_band), _ptr(geo2_band),
+                                                                    _ptr(fg_u_band), _ptr(fg_v_band), nx, ny, nc,
+                                                                    C.byref(p), _ptr(u_band), _ptr(v_band)))
+        else:
+            self._check(self._L.octane_variational_flow_band_dev(self._h, _ptr(geo1_band), _ptr(geo2_band), nx, ny, nc,
+                                                                 C.byref(p), _ptr(u_band), _ptr(v_band)))
         self._before_torch()
         return u_band, v_band
 

@@ -584,15 +584,18 @@ void begin_call(octane_ctx* c)
     c->event_next = 0;
 }
 
+// d_fg_u / d_fg_v: the first guess over the SAME rows as the images (the whole scene on one GPU, rows [in0,in1)
+// of a band), read only when p->first_guess; d_u / d_v: the owned rows of the flow, written.  On one GPU the
+// two are the same in/out buffers (the reference's uarr / varr, :1330-1335,1434-1438).
 int solve_dev(octane_ctx* c, const float* d_img1, const float* d_img2, int nx, int ny, int nc,
-              const octane_params* p, float* d_u, float* d_v)
+              const octane_params* p, const float* d_fg_u, const float* d_fg_v, float* d_u, float* d_v)
 {
     if (!c || !d_img1 || !d_img2 || !p || !d_u || !d_v) { set_err("null argument"); return OCTANE_EINVAL; }
-    if (c->comm.world > 1 && p->first_guess) { set_err("first guess is not supported in banded runs yet"); return OCTANE_EINVAL; }
+    if (p->first_guess && (!d_fg_u || !d_fg_v)) { set_err("first_guess is set but no first guess was given"); return OCTANE_EINVAL; }
     int rc = prepare(c, nx, ny, nc, *p);
     if (rc) return rc;
     Scope total(c, CAT_TOTAL);
-    rc = ingest(c, d_img1, d_img2, d_u, d_v);
+    rc = ingest(c, d_img1, d_img2, d_fg_u, d_fg_v);
     if (rc) return rc;
     rc = run_levels(c);
     if (rc) return rc;
@@ -831,15 +834,15 @@ int octane_variational_flow_dev(octane_ctx* c, const float* d_img1, const float*
     if (!c) return OCTANE_EINVAL;
     if (c->comm.world > 1) { set_err("context is banded: use octane_variational_flow_band_dev"); return OCTANE_EINVAL; }
     begin_call(c);
-    return solve_dev(c, d_img1, d_img2, nx, ny, nc, p, d_u, d_v);
+    return solve_dev(c, d_img1, d_img2, nx, ny, nc, p, d_u, d_v, d_u, d_v);
 }
 
-int octane_variational_flow_band_dev(octane_ctx* c, const float* d_img1, const float* d_img2, int nx, int ny, int nc,
-                                     const octane_params* p, float* d_u, float* d_v)
+namespace {
+int band_solve(octane_ctx* c, const float* d_img1, const float* d_img2, const float* d_fg_u, const float* d_fg_v,
+               int nx, int ny, int nc, const octane_params* p, float* d_u, float* d_v)
 {
-    if (!c) return OCTANE_EINVAL;
     begin_call(c);
-    int rc = solve_dev(c, d_img1, d_img2, nx, ny, nc, p, d_u, d_v);
+    int rc = solve_dev(c, d_img1, d_img2, nx, ny, nc, p, d_fg_u, d_fg_v, d_u, d_v);
     if (rc) return rc;
     if (c->comm.world > 1) {          // halo check needs the device flag
         CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -847,6 +850,28 @@ int octane_variational_flow_band_dev(octane_ctx* c, const float* d_img1, const f
         if (c->h_scal->comm_err) { set_err("a peer's partial sums did not arrive (peer-memory exchange timed out)"); return OCTANE_ECOMM; }
     }
     return OCTANE_OK;
+}
+}  // namespace
+
+int octane_variational_flow_band_dev(octane_ctx* c, const float* d_img1, const float* d_img2, int nx, int ny, int nc,
+                                     const octane_params* p, float* d_u, float* d_v)
+{
+    if (!c || !p) { set_err("null argument"); return OCTANE_EINVAL; }
+    if (p->first_guess && c->comm.world > 1) {
+        // the in/out buffers hold the owned rows only; the hint field needs the band's overlap rows too
+        set_err("banded runs take the first guess through octane_variational_flow_band_fg_dev (rows [in0,in1))");
+        return OCTANE_EINVAL;
+    }
+    return band_solve(c, d_img1, d_img2, d_u, d_v, nx, ny, nc, p, d_u, d_v);
+}
+
+int octane_variational_flow_band_fg_dev(octane_ctx* c, const float* d_img1, const float* d_img2, const float* d_fg_u,
+                                        const float* d_fg_v, int nx, int ny, int nc, const octane_params* p, float* d_u,
+                                        float* d_v)
+{
+    if (!c || !p) { set_err("null argument"); return OCTANE_EINVAL; }
+    if (!p->first_guess) { set_err("octane_variational_flow_band_fg_dev needs p->first_guess"); return OCTANE_EINVAL; }
+    return band_solve(c, d_img1, d_img2, d_fg_u, d_fg_v, nx, ny, nc, p, d_u, d_v);
 }
 
 int octane_variational_flow(octane_ctx* c, const float* img1, const float* img2, int nx, int ny, int nc,
@@ -869,7 +894,7 @@ int octane_variational_flow(octane_ctx* c, const float* img1, const float* img2,
         CUDA_OK(cudaMemcpyAsync(d_u, u, uv_bytes, cudaMemcpyHostToDevice, c->stream));
         CUDA_OK(cudaMemcpyAsync(d_v, v, uv_bytes, cudaMemcpyHostToDevice, c->stream));
     }
-    rc = solve_dev(c, d_i1, d_i2, nx, ny, nc, p, d_u, d_v);
+    rc = solve_dev(c, d_i1, d_i2, nx, ny, nc, p, d_u, d_v, d_u, d_v);
     if (rc) return rc;
     CUDA_OK(cudaMemcpyAsync(u, d_u, uv_bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaMemcpyAsync(v, d_v, uv_bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -916,7 +941,7 @@ int octane_optical_flow_dev(octane_ctx* c, const float* d_img1, const float* d_i
         if (rc) return rc;
     }
     begin_call(c);
-    int rc = solve_dev(c, d_img1, d_img2, nx, ny, nc, p, d_u, d_v);
+    int rc = solve_dev(c, d_img1, d_img2, nx, ny, nc, p, d_u, d_v, d_u, d_v);
     if (rc) return rc;
     if (p->doCTH) {                            // src/oct_optical_flow.cc:71-88
         launch_ctp_pack(d_cth, d_ctp, (size_t)nx * ny, p->ir == 1, c->stream);
@@ -979,7 +1004,7 @@ int octane_optical_flow(octane_ctx* c, const float* img1, const float* img2, con
         CUDA_OK(cudaMemcpyAsync(d_u, upix, fb, cudaMemcpyHostToDevice, c->stream));
         CUDA_OK(cudaMemcpyAsync(d_v, vpix, fb, cudaMemcpyHostToDevice, c->stream));
     }
-    rc = solve_dev(c, d_i1, d_i2, nx, ny, nc, p, d_u, d_v);
+    rc = solve_dev(c, d_i1, d_i2, nx, ny, nc, p, d_u, d_v, d_u, d_v);
     if (rc) return rc;
     if (p->doCTH || p->dosrsal) CUDA_OK(cudaMemcpyAsync(d_cth, cth, fb, cudaMemcpyHostToDevice, c->stream));
     if (p->doCTH) {                            // src/oct_optical_flow.cc:71-88

@@ -18,24 +18,34 @@ from octane_b200 import synthetic as S  # noqa: E402
 def main():
     nx, ny = int(sys.argv[1]), int(sys.argv[2])
     max_disp = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+    with_fg = len(sys.argv) > 4 and sys.argv[4] == "fg"        # first guess + hinting (-firstguess -lambdac 0.5)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    p = ob.default_params(max_disp=max_disp)
+    p = ob.default_params(max_disp=max_disp, first_guess=int(with_fg), lambdac=0.5 if with_fg else 0.0)
     ctx = ob.Context(local)
+
+    def first_guess(r0, r1):
+        """smooth displacement field close to the true drift, rows [r0, r1)"""
+        y = torch.arange(r0, r1, device=dev, dtype=torch.float32)[:, None]
+        x = torch.arange(nx, device=dev, dtype=torch.float32)[None, :]
+        return ((0.6 + 0.3 * torch.sin(x / 23.0) * torch.cos(y / 31.0)).contiguous(),
+                (-0.3 + 0.2 * torch.cos(x / 19.0 + y / 29.0)).contiguous())
+
     ids = [ob.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     ctx.comm_init(ids[0], rank, world)
     own0, own1, in0, in1 = ob.band_plan(nx, ny, p, rank, world)
     img1, img2 = S.make_pair_torch(nx, ny, 9, dev, rows=(in0, in1))
     u = torch.zeros((own1 - own0, nx), device=dev); v = torch.zeros_like(u)
-    ctx.oct_variational_optical_flow_band(img1, img2, u, v, nx, ny, p)
+    fgu, fgv = first_guess(in0, in1) if with_fg else (None, None)
+    ctx.oct_variational_optical_flow_band(img1, img2, u, v, nx, ny, p, fg_u_band=fgu, fg_v_band=fgv)
     ctx.synchronize()
     st = ctx.stats()
     # second run: bit-reproducible for a fixed world size
     u2 = torch.zeros_like(u); v2 = torch.zeros_like(v)
-    ctx.oct_variational_optical_flow_band(img1, img2, u2, v2, nx, ny, p)
+    ctx.oct_variational_optical_flow_band(img1, img2, u2, v2, nx, ny, p, fg_u_band=fgu, fg_v_band=fgv)
     ctx.synchronize()
     repro = bool(torch.equal(u, u2) and torch.equal(v, v2))
     # navigation of the band
@@ -55,7 +65,9 @@ def main():
         c1 = ob.Context(local)
         a, b = S.make_pair_torch(nx, ny, 9, dev)
         u1 = torch.zeros((ny, nx), device=dev); v1 = torch.zeros_like(u1)
-        c1.oct_variational_optical_flow(a, b, u1, v1, ob.default_params(max_disp=max_disp))
+        if with_fg:
+            u1, v1 = first_guess(0, ny)
+        c1.oct_variational_optical_flow(a, b, u1, v1, p)
         s1 = [torch.zeros((ny, nx), dtype=torch.int16, device=dev) for _ in range(4)]
         c1.oct_pix2uv_cuda(nav, 0.0, dt, u1, v1, *s1, p)
         c1.synchronize()

@@ -148,3 +148,23 @@ def test_reference_signatures_of_regridding_and_srsal_drop_in(oracle):
     wu, wv = oracle.srsal(u, v, cth)
     np.testing.assert_allclose(su, wu, **SRSAL_TOL)
     np.testing.assert_allclose(sv, wv, **SRSAL_TOL)
+
+
+def test_band_first_guess_entry_point_on_one_gpu(ctx):
+    """octane_variational_flow_band_fg_dev at world size 1 (band == scene): separate first-guess input and flow output
+    buffers give the bits of the in/out entry point (the multi-GPU case is tests/test_gpu_band.py)"""
+    import torch
+    c = cases.VARIATIONAL["var_160x120_fg"]
+    img1, img2, u0, v0 = cases.variational_inputs(c)
+    ny, nx = img1.shape
+    p = ob.default_params(first_guess=1, **c["params"])
+    u, v = u0.copy(), v0.copy()
+    ctx.oct_variational_optical_flow(img1, img2, u, v, p)
+    ub = torch.zeros((ny, nx), device="cuda"); vb = torch.zeros_like(ub)
+    fgu, fgv = dev(u0), dev(v0)
+    ctx.oct_variational_optical_flow_band(dev(img1), dev(img2), ub, vb, nx, ny, p, fg_u_band=fgu, fg_v_band=fgv)
+    ctx.synchronize()
+    assert np.array_equal(ub.cpu().numpy(), u) and np.array_equal(vb.cpu().numpy(), v)
+    assert np.array_equal(fgu.cpu().numpy(), u0)            # the first guess is an input only
+    g = load_golden("var_160x120_fg")
+    assert np.abs(u - g["u"]).max() < 1e-2
