@@ -21,6 +21,19 @@ struct Geom {
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Function attributes (dynamic shared-memory limits) are per device: `mask` remembers the devices a launch
+// site has already configured (one bit per device; setting an attribute twice is harmless, so a race
+// between host threads is benign).  Returns true the first time the current device is seen.
+inline bool first_launch_on_device(unsigned long long* mask)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (*mask & bit) return false;
+    *mask |= bit;
+    return true;
+}
+
 // Device-side scalars of one PCG solve (reference: rkTzk, pkTApk, zktrk,
 // z0tr0, residc -- managed floats, src/oct_variational_optical_flow.cu:1319-1328).
 struct PcgScalars {

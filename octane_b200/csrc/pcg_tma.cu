@@ -414,15 +414,14 @@ void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, in
     const size_t smem = (size_t)NSTAGE * STAGE_FLOATS * sizeof(float);
     // developer switch: pixels per consumer thread (2 -> 16 consumer warps, 4 -> 8)
     static const int px = (getenv("OCTANE_P1_PX") && atoi(getenv("OCTANE_P1_PX")) == 4) ? 4 : 2;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long configured = 0;
+    if (first_launch_on_device(&configured)) {
         cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
     }
     const int xm = ki == 0 ? XM_NONE : (ki == 1 ? XM_INIT : XM_ACC);
     if (px == 2) {

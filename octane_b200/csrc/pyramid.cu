@@ -168,11 +168,9 @@ void launch_blur_decimate(const float* src, const Geom& gs, float* dst, const Ge
     const int nrow_h = (TY - 1) * step + 2 * R + 2;
     const size_t smem = sizeof(float) * ((size_t)nrow_h * TX + 2 * R + 1);
     dim3 grid((gd.nx + TX - 1) / TX, (jb - ja + TY - 1) / TY, nc), block(TX, TY);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long configured = 0;
+    if (first_launch_on_device(&configured))
         cudaFuncSetAttribute(k_blur_decimate<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_set = true;
-    }
     k_blur_decimate<TX, TY><<<grid, block, smem, st>>>(src, gs, dst, gd, ja, jb, factor, GK, R, scale, nc);
 }
 
