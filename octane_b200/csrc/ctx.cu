@@ -661,7 +661,8 @@ void collect_stats(octane_ctx* c)
     octane_stats& s = c->stats;
     const Plan& pl = c->plan;
     memset(&s, 0, sizeof s);
-    if (!c->plan_valid) return;
+    s.kernel_launches = c->launches;
+    if (!c->plan_valid) return;             // the context has only run ingest / regridding / post stages so far
     s.n_levels = (int)pl.lv.size();
     s.n_solves = pl.p.kiters * 3 * pl.p.liters;
     double bytes = 0.0;
