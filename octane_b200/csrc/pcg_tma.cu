@@ -84,6 +84,11 @@ template <> __device__ __forceinline__ Px<2> ldv<2>(const float* p)
     const float2 t = *reinterpret_cast<const float2*>(p);
     Px<2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
 }
+template <> __device__ __forceinline__ Px<1> ldv<1>(const float* p)
+{
+    Px<1> r; r.v[0] = *p; return r;
+}
+__device__ __forceinline__ void stv(float* p, const Px<1>& a) { *p = a.v[0]; }
 __device__ __forceinline__ void stv(float* p, const Px<4>& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
 __device__ __forceinline__ void stv(float* p, const Px<2>& a) { *reinterpret_cast<float2*>(p) = make_float2(a.v[0], a.v[1]); }
 template <int PX> __device__ __forceinline__ Px<PX> zerov()
@@ -181,12 +186,15 @@ __device__ __forceinline__ PRowT<PX> p_from_stage(const float* st, int i0s, int 
 
 // The stencil row is latency-bound per warp (dependent FMA chains, shared-memory loads, shuffles),
 // so what keeps the copy engine busy is the number of consumer warps: PX = 2 runs 16 of them
-// (512 threads x 2 pixels), PX = 4 runs 8.
+// (512 threads x 2 pixels), PX = 4 runs 8.  PX = 1 (experimental, OCTANE_P1_PX=1, not measured yet) runs 31:
+// 992 consumer threads + the producer warp fill the 1024-thread block, strips are at most 992 pixels wide.
+template <int PX> struct Consumers { static constexpr int N = SWMAX / PX; };
+template <> struct Consumers<1> { static constexpr int N = SWMAX - 32; };
 template <int XM, int PX>
-__global__ void __launch_bounds__(SWMAX / PX + 32, 1) k_pcg_pass1_tma(TArgs a)
+__global__ void __launch_bounds__(Consumers<PX>::N + 32, 1) k_pcg_pass1_tma(TArgs a)
 {
     constexpr bool FIRST = (XM == XM_NONE);
-    constexpr int CONSUMERS = SWMAX / PX;
+    constexpr int CONSUMERS = Consumers<PX>::N;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red[32];
     __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE];
@@ -390,10 +398,14 @@ void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, in
     // developer switches for layout experiments: forced strip width / rows per task
     static const int force_sw = getenv("OCTANE_P1_SW") ? atoi(getenv("OCTANE_P1_SW")) : 0;
     static const int force_rs = getenv("OCTANE_P1_RS") ? atoi(getenv("OCTANE_P1_RS")) : 0;
-    a.nstrips = (g.nx + SWMAX - 1) / SWMAX;
+    // developer switch: pixels per consumer thread (2 -> 16 consumer warps, 4 -> 8, 1 -> 31 with 992-pixel strips)
+    static const int px_env = getenv("OCTANE_P1_PX") ? atoi(getenv("OCTANE_P1_PX")) : 2;
+    static const int px = (px_env == 4 || px_env == 1) ? px_env : 2;
+    const int swmax = (px == 1) ? Consumers<1>::N : SWMAX;
+    a.nstrips = (g.nx + swmax - 1) / swmax;
     a.sw = round_up((g.nx + a.nstrips - 1) / a.nstrips, 32);
-    if (a.sw > SWMAX) a.sw = SWMAX;
-    if (force_sw >= 32 && force_sw <= SWMAX) a.sw = round_up(force_sw, 32);
+    if (a.sw > swmax) a.sw = swmax;
+    if (force_sw >= 32 && force_sw <= swmax) a.sw = round_up(force_sw, 32);
     a.nstrips = (g.nx + a.sw - 1) / a.sw;
     // rows per task: minimise rounds x (rows + 2 halo rows) over the persistent grid
     const int nrows = jb - ja;
@@ -412,8 +424,6 @@ void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, in
     int grid = ntasks < sm_count ? ntasks : sm_count;
     if (grid > b.max_partial_blocks) grid = b.max_partial_blocks;
     const size_t smem = (size_t)NSTAGE * STAGE_FLOATS * sizeof(float);
-    // developer switch: pixels per consumer thread (2 -> 16 consumer warps, 4 -> 8)
-    static const int px = (getenv("OCTANE_P1_PX") && atoi(getenv("OCTANE_P1_PX")) == 4) ? 4 : 2;
     static unsigned long long configured = 0;
     if (first_launch_on_device(&configured)) {
         cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -422,6 +432,9 @@ void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, in
         cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     const int xm = ki == 0 ? XM_NONE : (ki == 1 ? XM_INIT : XM_ACC);
     if (px == 2) {
@@ -429,6 +442,11 @@ void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, in
         if (xm == XM_NONE)      k_pcg_pass1_tma<XM_NONE, 2><<<grid, threads, smem, st>>>(a);
         else if (xm == XM_INIT) k_pcg_pass1_tma<XM_INIT, 2><<<grid, threads, smem, st>>>(a);
         else                    k_pcg_pass1_tma<XM_ACC, 2><<<grid, threads, smem, st>>>(a);
+    } else if (px == 1) {
+        const int threads = Consumers<1>::N + 32;
+        if (xm == XM_NONE)      k_pcg_pass1_tma<XM_NONE, 1><<<grid, threads, smem, st>>>(a);
+        else if (xm == XM_INIT) k_pcg_pass1_tma<XM_INIT, 1><<<grid, threads, smem, st>>>(a);
+        else                    k_pcg_pass1_tma<XM_ACC, 1><<<grid, threads, smem, st>>>(a);
     } else {
         const int threads = SWMAX / 4 + 32;
         if (xm == XM_NONE)      k_pcg_pass1_tma<XM_NONE, 4><<<grid, threads, smem, st>>>(a);
