@@ -269,6 +269,16 @@ def ref_zoom_out_float(field, factor, cnum=0, L=None):
     return out.reshape(nyy, nxx) if cnum == 0 else out
 
 
+def ref_zoom_out(field, factor):
+    """the reference's CPU pyramid stage in double (oct_zoom_out, src/oct_zoom.cc:17): blur + bicubic sampling"""
+    field = np.ascontiguousarray(field, np.float64)
+    ny, nx = field.shape
+    nxx, nyy = zoom_out_size(nx, ny, factor)
+    out = np.zeros((nyy, nxx), np.float64)
+    ref_cpu().ref_zoom_out(field, out, nx, ny, float(factor))
+    return out
+
+
 def srsal(u, v, cth):
     """-srsal bilateral post-smoother restated (src/oct_srsal_cuda.cu:35-71)"""
     u = np.array(u, np.float32, order="C"); v = np.array(v, np.float32, order="C")

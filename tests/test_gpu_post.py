@@ -38,6 +38,20 @@ def test_zoom_out_float_is_bit_identical_to_oracle_and_reference(ctx, oracle, na
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("factor", [0.5, 0.25, 0.125])
+def test_zoom_out_equals_the_reference_cpu_pyramid_stage_on_config_1(ctx, oracle, factor):
+    """BASELINE config 1: the 500 x 500 texture through the reference's CPU pyramid stage oct_zoom_out (double,
+    src/oct_zoom.cc:17) -- the kernel's float output is that double result rounded once"""
+    from octane_b200 import synthetic as S
+    i1, _, _, _ = S.make_pair(500, 500, seed=1, kind="shift", drift=(2.0, -1.0))
+    got = ctx.oct_zoom_out_float(i1, factor)
+    try:
+        want = oracle.ref_zoom_out(i1, factor).astype(np.float32)
+    except OSError:
+        pytest.skip("oracle/_ref/libref_cpu.so not built")
+    assert np.array_equal(got, want)
+
+
 def test_zoom_out_float_large_field_properties(ctx):
     """a 0.5 km mesoscale channel (2000 x 2000) down to the 2 km grid: constant in -> the same constant scale
     everywhere (dropped tap), and blur + decimation commutes with a shift by whole output pixels in the interior"""

@@ -55,6 +55,19 @@ def test_zoom_out_integer_ratio_is_blur_then_decimation(oracle):
     assert out.shape == (30, 40) and np.isfinite(out).all()
 
 
+@pytest.mark.parametrize("factor", [0.5, 0.25, 0.125])
+def test_zoom_out_equals_the_reference_cpu_pyramid_stage_on_config_1(oracle, factor):
+    """BASELINE config 1 (500 x 500 cloud texture through the reference's CPU pyramid / zoom): oct_zoom_out (double,
+    src/oct_zoom.cc:17) and oct_zoom_out_float are the same arithmetic; on float input the float restatement is the
+    double result rounded once"""
+    _ref_or_skip(oracle)
+    from octane_b200 import synthetic as S
+    i1, _, _, _ = S.make_pair(500, 500, seed=1, kind="shift", drift=(2.0, -1.0))
+    want = oracle.ref_zoom_out(i1, factor).astype(np.float32)
+    got = oracle.zoom_out_float(i1, factor)
+    assert got.shape == (int(500 * factor + 0.5),) * 2 and np.array_equal(got, want)
+
+
 def _reflect(x, n):
     x = np.where(x < 0, -x, x)
     return np.where(x >= n, n - (x - n + 1), x)
