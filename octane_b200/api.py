@@ -108,6 +108,29 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
+_NP = {"float32": np.float32, "int16": np.int16}
+
+
+def _require(what: str, a, dtype: str, cuda: Optional[bool] = None):
+    """The C ABI takes raw pointers: refuse anything that is not a C-contiguous array / tensor of the expected
+    element type (a float64 or strided array would be read as garbage, not converted).  cuda=True / False also pins
+    where a torch tensor lives (device-pointer vs host-buffer entry points).  None passes (optional arguments)."""
+    if a is None:
+        return
+    if _is_torch(a):
+        ok = str(a.dtype) == "torch." + dtype and a.is_contiguous()
+        where = "cuda" if a.is_cuda else "cpu"
+        if ok and cuda is not None and a.is_cuda != cuda:
+            raise TypeError(f"{what}: tensor lives on the {where}, this entry point needs {'CUDA' if cuda else 'host'} memory")
+    else:
+        ok = isinstance(a, np.ndarray) and a.dtype == _NP[dtype] and a.flags["C_CONTIGUOUS"]
+        if ok and cuda:
+            raise TypeError(f"{what}: numpy array given to a device-pointer entry point")
+    if not ok:
+        raise TypeError(f"{what}: expected a C-contiguous {dtype} array, got {type(a).__name__} "
+                        f"{getattr(a, 'dtype', '?')}{'' if getattr(a, 'ndim', 0) == 0 else ' (strided?)'}")
+
+
 def _ptr(x):
     if x is None:
         return None
@@ -200,13 +223,13 @@ class Context:
         p = p or default_params()
         ny, nx = geo1.shape[-2:]
         dev = _is_torch(geo1)
+        for name, a in (("geo1", geo1), ("geo2", geo2), ("u", u), ("v", v)):
+            _require(name, a, "float32", cuda=dev)
         if dev:
             fn = self._L.octane_variational_flow_dev
             self._after_torch()
         else:
             fn = self._L.octane_variational_flow
-            for a in (geo1, geo2, u, v):
-                assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
         self._check(fn(self._h, _ptr(geo1), _ptr(geo2), nx, ny, nc, C.byref(p), _ptr(u), _ptr(v)))
         if dev:
             self._before_torch()
@@ -216,6 +239,9 @@ class Context:
                                           fg_u_band=None, fg_v_band=None):
         """row-band solve (collective).  geo*_band and the optional first guess fg_*_band hold rows [in0,in1) of
         band_plan(); u_band / v_band receive rows [own0,own1)."""
+        for name, a in (("geo1_band", geo1_band), ("geo2_band", geo2_band), ("u_band", u_band), ("v_band", v_band),
+                        ("fg_u_band", fg_u_band), ("fg_v_band", fg_v_band)):
+            _require(name, a, "float32", cuda=True)
         self._after_torch()
         if p.first_guess and fg_u_band is not None:
             self._check(self._L.octane_variational_flow_band_fg_dev(self._h, _ptr(geo1_band), _ptr(geo2_band),
@@ -231,7 +257,12 @@ class Context:
         """Returns (dT, moved): moved=True when the sector-moved guard zeroed the outputs."""
         p = p or default_params()
         ny, nx = u.shape
-        if _is_torch(u):
+        dev = _is_torch(u)
+        for name, a in (("u", u), ("v", v)):
+            _require(name, a, "float32", cuda=dev)
+        for name, a in (("ur", ur), ("vr", vr), ("ur2", ur2), ("vr2", vr2)):
+            _require(name, a, "int16", cuda=dev)
+        if dev:
             self._after_torch()
             rc = self._check(self._L.octane_pix2uv_dev(self._h, C.byref(nav), t1, t2, _ptr(u), _ptr(v), nx, ny,
                                                        C.byref(p), _ptr(ur), _ptr(vr), _ptr(ur2), _ptr(vr2)))
@@ -243,6 +274,10 @@ class Context:
         return dT.value, rc == 1
 
     def oct_pix2uv_band(self, nav: Nav, t1, t2, u, v, nx, row0, nrows, ur, vr, ur2, vr2, p: Params):
+        for name, a in (("u", u), ("v", v)):
+            _require(name, a, "float32", cuda=True)
+        for name, a in (("ur", ur), ("vr", vr), ("ur2", ur2), ("vr2", vr2)):
+            _require(name, a, "int16", cuda=True)
         self._after_torch()
         rc = self._check(self._L.octane_pix2uv_band_dev(self._h, C.byref(nav), t1, t2, _ptr(u), _ptr(v), nx, row0,
                                                         nrows, C.byref(p), _ptr(ur), _ptr(vr), _ptr(ur2), _ptr(vr2)))
@@ -264,6 +299,11 @@ class Context:
         ctp = out.get("CTP") if p.doCTH else None
         if p.doCTH and ctp is None:
             ctp = np.zeros((ny, nx), np.int16)
+        for name, a in (("geo1", geo1), ("geo2", geo2), ("cth", cth), ("upix", upix), ("vpix", vpix)):
+            _require(name, a, "float32", cuda=False)
+        for name in ("uVal", "vVal", "uVal2", "vVal2"):
+            _require(name, out[name], "int16", cuda=False)
+        _require("CTP", ctp, "int16", cuda=False)
         dT = C.c_float()
         self._check(self._L.octane_optical_flow(self._h, _ptr(geo1), _ptr(geo2), _ptr(cth), nx, ny, nc, C.byref(nav),
                                                 t1, t2, C.byref(p), _ptr(upix), _ptr(vpix), _ptr(out["uVal"]),
@@ -278,6 +318,10 @@ class Context:
         sync_torch=False skips the ordering against torch's current stream (the caller keeps several contexts
         in flight and orders them itself: batch mode)."""
         ny, nx = geo1.shape[-2:]
+        for name, a in (("geo1", geo1), ("geo2", geo2), ("cth", cth), ("upix", upix), ("vpix", vpix)):
+            _require(name, a, "float32", cuda=True)
+        for name, a in (("ur", ur), ("vr", vr), ("ur2", ur2), ("vr2", vr2), ("ctp", ctp)):
+            _require(name, a, "int16", cuda=True)
         if sync_torch:
             self._after_torch()
         rc = self._check(self._L.octane_optical_flow_dev(self._h, _ptr(geo1), _ptr(geo2), _ptr(cth), nx, ny, nc, C.byref(nav),
@@ -366,7 +410,11 @@ class Context:
     def oct_srsal_cu(self, upix, vpix, cth):
         """-srsal bilateral post-smoother, in place on upix / vpix (oct_srsal_cu, src/oct_srsal_cuda.cu:73)"""
         ny, nx = upix.shape
-        if _is_torch(upix):
+        dev = _is_torch(upix)
+        _require("upix", upix, "float32", cuda=dev)
+        _require("vpix", vpix, "float32", cuda=dev)
+        if dev:
+            _require("cth", cth, "float32", cuda=True)
             self._after_torch()
             self._check(self._L.octane_srsal_dev(self._h, _ptr(upix), _ptr(vpix), _ptr(cth), nx, ny))
             return upix, vpix

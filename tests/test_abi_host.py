@@ -180,3 +180,21 @@ def test_band_table_matches_reference_values():
     assert ob.band_minmax(7) == (2.0, 0.0) and ob.band_minmax(8) == (6.0, 3.0)    # the "meteorological" ranges
     with pytest.raises(ob.OctaneError):
         ob.band_minmax(17)
+
+
+def test_host_mirror_refuses_arrays_the_abi_would_misread():
+    """the C ABI takes raw pointers: the Python mirror rejects wrong element types, strided views and host / device
+    mix-ups before anything reaches the library (octane_b200.api._require)"""
+    import torch
+    from octane_b200.api import _require
+    a = np.zeros((4, 6), np.float32)
+    _require("a", a, "float32"); _require("a", a, "float32", cuda=False); _require("none", None, "int16", cuda=True)
+    _require("s", np.zeros((2, 2), np.int16), "int16")
+    t = torch.zeros((4, 6))
+    _require("t", t, "float32", cuda=False)
+    bad = [(a.astype(np.float64), "float32", None), (a[:, ::2], "float32", None), (a.T, "float32", None),
+           ([1.0, 2.0], "float32", None), (a, "float32", True), (a, "int16", None),
+           (t, "float32", True), (t.double(), "float32", None), (t.t(), "float32", None), (t, "int16", None)]
+    for x, dt, cuda in bad:
+        with pytest.raises(TypeError):
+            _require("x", x, dt, cuda=cuda)
