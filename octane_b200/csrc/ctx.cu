@@ -104,6 +104,11 @@ int make_plan(Plan& pl, int nx, int ny, int nc, const octane_params& p, int rank
         int xi, yi;
         zoom_size(nx, ny, L.factor, &xi, &yi);
         if (xi < 4 || yi < 4) { set_err("pyramid level smaller than 4 pixels"); return OCTANE_EINVAL; }
+        if (k < K - 1 && blur_decimate_smem_bytes(L.factor, L.R) > BLUR_DECIMATE_SMEM_LIMIT) {
+            // the blur stages (8-1)/factor + 2R + 2 full-resolution rows of a 32-column tile per block
+            set_err("pyramid too deep: the coarsest level's blur footprint exceeds shared memory (use fewer levels)");
+            return OCTANE_EINVAL;
+        }
         L.lambdac = (float)((double)lambdaco * pow(0.5, k));  // :494
         L.own0 = (int)((long long)rank * yi / world);
         L.own1 = (int)((long long)(rank + 1) * yi / world);

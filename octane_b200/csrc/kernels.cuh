@@ -60,6 +60,11 @@ void launch_build(const LevelFields& f, const PcgBuffers& b, const Geom& g, int 
                   const BuildParams& bp, int halo_check, cudaStream_t st);
 int build_partial_blocks(const Geom& g, int nrows);
 
+// shared memory one block of k_blur_decimate needs for a level (pyramid.cu); levels beyond the limit are refused
+// when the plan is made instead of failing at launch
+constexpr size_t BLUR_DECIMATE_SMEM_LIMIT = 160 * 1024;
+size_t blur_decimate_smem_bytes(float factor, int R);
+
 // ---- pcg.cu
 // One PCG iteration ki = pass1 (x += alpha_{ki-1} p_{ki-1}; p = z + beta p; q = A p; dot p.q)
 // + pass2 (r -= alpha q, dots r.r and z.r, stop rule).  The x update of an iteration rides

@@ -159,18 +159,24 @@ void launch_fill_gk(float* GK, float factor, int R, cudaStream_t st)
     k_fill_gk<<<1, 32, 0, st>>>(GK, factor, R);
 }
 
+size_t blur_decimate_smem_bytes(float factor, int R)
+{
+    constexpr int TX = 32, TY = 8;
+    const int step = (int)(1.0f / factor) + 1;
+    const int nrow_h = (TY - 1) * step + 2 * R + 2;
+    return sizeof(float) * ((size_t)nrow_h * TX + 2 * R + 1);
+}
+
 void launch_blur_decimate(const float* src, const Geom& gs, float* dst, const Geom& gd, int ja, int jb,
                           float factor, const float* GK, int R, float scale, int nc, cudaStream_t st)
 {
     if (jb <= ja) return;
     constexpr int TX = 32, TY = 8;
-    const int step = (int)(1.0f / factor) + 1;
-    const int nrow_h = (TY - 1) * step + 2 * R + 2;
-    const size_t smem = sizeof(float) * ((size_t)nrow_h * TX + 2 * R + 1);
+    const size_t smem = blur_decimate_smem_bytes(factor, R);
     dim3 grid((gd.nx + TX - 1) / TX, (jb - ja + TY - 1) / TY, nc), block(TX, TY);
     static unsigned long long configured = 0;
     if (first_launch_on_device(&configured))
-        cudaFuncSetAttribute(k_blur_decimate<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_blur_decimate<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLUR_DECIMATE_SMEM_LIMIT);
     k_blur_decimate<TX, TY><<<grid, block, smem, st>>>(src, gs, dst, gd, ja, jb, factor, GK, R, scale, nc);
 }
 

@@ -198,3 +198,21 @@ def test_host_mirror_refuses_arrays_the_abi_would_misread():
     for x, dt, cuda in bad:
         with pytest.raises(TypeError):
             _require("x", x, dt, cuda=cuda)
+
+
+def test_plans_that_cannot_run_are_refused_on_the_host():
+    """octane_workspace_bytes makes the same plan a solve would: 0 + octane_last_error for parameter sets the
+    kernels cannot run (reference: no checks at all, src/oct_variational_optical_flow.cu:1229-1266)"""
+    import ctypes as C
+    L = _lib.load()
+
+    def ws(nx, ny, nc=1, **kw):
+        p = ob.default_params(**kw)
+        return L.octane_workspace_bytes(nx, ny, nc, C.byref(p))
+
+    assert ws(21696, 21696) > 40 * 2**30 and ws(21696, 21696, 3) < 90 * 2**30      # 108 B/px and the 3-channel case fit 180 GB
+    assert ws(21696, 21696, kiters=8) > 0
+    assert ws(21696, 21696, kiters=9) == 0 and b"pyramid too deep" in L.octane_last_error()
+    assert ws(20, 20) == 0 and b"smaller than 4 pixels" in L.octane_last_error()      # 20 * 0.125 = 3 (rounded)
+    assert ws(64, 64, 4) == 0 and ws(64, 64, alpha=0.0) == 0 and ws(64, 64, scaleF=1.0) == 0
+    assert ws(64, 64, kiters=4, liters=30) == 0                                        # more than OCTANE_MAX_SOLVES solves
