@@ -168,6 +168,8 @@ struct octane_ctx {
     cudaEvent_t ev_stage = nullptr;
     bool profile = false, graphs = true;
     bool use_tma = getenv("OCTANE_NO_TMA") == nullptr;   // developer switch: v1 pass-1 kernel everywhere
+    // experimental (not measured yet): the first GNC stage's solves skip the constant W / N planes in pass 1
+    bool const_wn = getenv("OCTANE_CONST_WN") != nullptr;
     Comm comm;
     // workspace
     char* arena = nullptr;
@@ -175,7 +177,7 @@ struct octane_ctx {
     Plan plan;
     bool plan_valid = false;
     Buffers buf;
-    std::vector<cudaGraphExec_t> pcg_graph;   // one per level
+    std::vector<cudaGraphExec_t> pcg_graph;   // two per level: [2 * level + (constant W / N variant)]
     // small persistent device objects
     PcgScalars* d_scal = nullptr;
     double* d_pending = nullptr;
@@ -323,7 +325,7 @@ int prepare(octane_ctx* c, int nx, int ny, int nc, const octane_params& p)
     c->buf.pcg.p2p.epoch = c->comm.d_epoch;
     c->buf.pcg.up_ru = c->buf.pcg.up_rv = c->buf.pcg.dn_ru = c->buf.pcg.dn_rv = nullptr;
     c->plan = pl;
-    c->pcg_graph.assign(pl.lv.size(), nullptr);
+    c->pcg_graph.assign(2 * pl.lv.size(), nullptr);
     c->plan_valid = true;
     return OCTANE_OK;
 }
@@ -385,7 +387,7 @@ int allreduce_pending(octane_ctx* c, int n)
 }
 
 // ---- the PCG loop of one solve (:1129-1182), enqueued or captured ----------------------
-int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve)
+int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve, int const_wn)
 {
     PcgBuffers b = c->buf.pcg;
     const int iters = c->plan.p.cgiters;
@@ -399,7 +401,7 @@ int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve)
         {
             Scope s(c, CAT_P1, level, solve, ki);
             if (c->use_tma && pcg_pass1_tma_usable(L.g, L.own1 - L.own0))
-                launch_pcg_pass1_tma(b, L.g, L.own0, L.own1, ki, multi, c->sm_count, c->stream);
+                launch_pcg_pass1_tma(b, L.g, L.own0, L.own1, ki, multi, c->sm_count, c->stream, const_wn);
             else
                 launch_pcg_pass1(b, L.g, L.own0, L.own1, ki, multi, c->sm_count, c->stream);
             c->launches++;
@@ -423,15 +425,17 @@ int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve)
     return OCTANE_OK;
 }
 
-int run_pcg(octane_ctx* c, const Level& L, int level, int solve)
+// const_wn: the system was built in the first GNC stage (W = N = -1 everywhere) and the context opted in
+int run_pcg(octane_ctx* c, const Level& L, int level, int solve, int const_wn)
 {
     if (c->plan.p.cgiters <= 0) return OCTANE_OK;
-    if (!c->graphs || c->profile) return enqueue_pcg(c, L, level, solve);
-    if (!c->pcg_graph[level]) {
+    if (!c->graphs || c->profile) return enqueue_pcg(c, L, level, solve, const_wn);
+    const size_t slot = 2 * (size_t)level + (const_wn ? 1 : 0);
+    if (!c->pcg_graph[slot]) {
         cudaGraph_t graph = nullptr;
         const long long before = c->launches;
         CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_pcg(c, L, level, solve);
+        int rc = enqueue_pcg(c, L, level, solve, const_wn);
         cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
         c->launches = before;
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -440,9 +444,9 @@ int run_pcg(octane_ctx* c, const Level& L, int level, int solve)
         e = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) { set_err("cudaGraphInstantiate: %s", cudaGetErrorString(e)); return OCTANE_ECUDA; }
-        c->pcg_graph[level] = exec;
+        c->pcg_graph[slot] = exec;
     }
-    CUDA_OK(cudaGraphLaunch(c->pcg_graph[level], c->stream));
+    CUDA_OK(cudaGraphLaunch(c->pcg_graph[slot], c->stream));
     c->launches += (long long)c->plan.p.cgiters * ((c->comm.world > 1 && !c->comm.p2p) ? 4 : 2);
     return OCTANE_OK;
 }
@@ -531,7 +535,7 @@ int run_levels(octane_ctx* c)
                         launch_finalize(B.pcg, FINALIZE_BUILD, bp.tol, st); c->launches++;
                     }
                 }
-                int rc = run_pcg(c, L, k, solve);
+                int rc = run_pcg(c, L, k, solve, (c->const_wn && gnc == 0) ? 1 : 0);
                 if (rc) return rc;
                 {
                     Scope s(c, CAT_UPDATE, k, solve);             // :1185-1195
@@ -1618,7 +1622,7 @@ int octane_stage_pcg(octane_ctx* c, const float* d_coef, const float* d_bu, cons
     CUDA_OK(cudaMemsetAsync(B.u, 0, (size_t)g.plane * sizeof(float), st));
     CUDA_OK(cudaMemsetAsync(B.v, 0, (size_t)g.plane * sizeof(float), st));
     begin_call(c);
-    rc = run_pcg(c, L, 0, 0); if (rc) return rc;
+    rc = run_pcg(c, L, 0, 0, 0); if (rc) return rc;
     launch_update_uv(B.u, B.v, B.pcg, g, 0, yi, c->d_its, c->sm_count, st);   // u = 0 + x
     if ((rc = copy_out(c, d_xu, B.u, g))) return rc;
     if ((rc = copy_out(c, d_xv, B.v, g))) return rc;

@@ -75,8 +75,9 @@ void launch_pcg_pass1(const PcgBuffers& b, const Geom& g, int ja, int jb, int ki
                       int sm_count, cudaStream_t st);
 // large levels: persistent TMA-fed variant of pass 1 (pcg_tma.cu)
 bool pcg_pass1_tma_usable(const Geom& g, int nrows);
+// const_wn: the system comes from the first GNC stage, whose W and N planes are -1 everywhere (experimental)
 void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, int ki, int store_halo,
-                          int sm_count, cudaStream_t st);
+                          int sm_count, cudaStream_t st, int const_wn = 0);
 void launch_pcg_pass2(const PcgBuffers& b, const Geom& g, int ja, int jb, int sm_count, cudaStream_t st);
 // u += x + alpha_last p_last, v likewise (:1185-1195 with the pending x term folded in)
 void launch_update_uv(float* u, float* v, const PcgBuffers& b, const Geom& g, int ja, int jb,

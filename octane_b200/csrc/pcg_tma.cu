@@ -190,7 +190,11 @@ __device__ __forceinline__ PRowT<PX> p_from_stage(const float* st, int i0s, int 
 // 992 consumer threads + the producer warp fill the 1024-thread block, strips are at most 992 pixels wide.
 template <int PX> struct Consumers { static constexpr int N = SWMAX / PX; };
 template <> struct Consumers<1> { static constexpr int N = SWMAX - 32; };
-template <int XM, int PX>
+// CWN (experimental, OCTANE_CONST_WN=1, not measured yet): in the first GNC stage the build stores W = N = -1 at
+// every pixel (al1 = 1: the couplings are -(1 + 0 * psi), build.cu), so the solves of that stage need not read the
+// two planes at all: 8 of pass 1's 68 B/px in a third of the solves.  The boundary multipliers mul_lo / mul_hi
+// zero the couplings that leave the scene, exactly as they do for the stored planes.
+template <int XM, int PX, bool CWN>
 __global__ void __launch_bounds__(Consumers<PX>::N + 32, 1) k_pcg_pass1_tma(TArgs a)
 {
     constexpr bool FIRST = (XM == XM_NONE);
@@ -233,19 +237,19 @@ __global__ void __launch_bounds__(Consumers<PX>::N + 32, 1) k_pcg_pass1_tma(TArg
                     float* st = stages + (size_t)stg * STAGE_FLOATS;
                     const bool centre = jr >= j_a && jr < j_b;
                     const bool need_n = jr < j_b;                    // own rows and the row above them
-                    const uint32_t nh = (FIRST ? 4u : 6u) + (centre ? 1u : 0u);
-                    const uint32_t ncb = (centre ? 1u : 0u) + (need_n ? 1u : 0u) + ((centre && XM == XM_ACC) ? 2u : 0u);
+                    const uint32_t nh = (FIRST ? 4u : 6u) + ((centre && !CWN) ? 1u : 0u);
+                    const uint32_t ncb = (centre ? 1u : 0u) + ((need_n && !CWN) ? 1u : 0u) + ((centre && XM == XM_ACC) ? 2u : 0u);
                     mbar_expect_tx(&full_bar[stg], nh * hb + ncb * cb);
                     const size_t row = g.at(0, jr);
 #pragma unroll
                     for (int q = 0; q < NHALO; q++) {
                         if (FIRST && (q == 2 || q == 3)) continue;
-                        if (q == 6 && !centre) continue;
+                        if (q == 6 && (!centre || CWN)) continue;
                         bulk_g2s(st + q * HA + (h0 - (i0s - HALO)), src_h[q] + row + h0, hb, &full_bar[stg]);
                     }
                     float* cst = st + NHALO * HA;
                     if (centre) bulk_g2s(cst, a.b.coef[C_A2] + row + i0s, cb, &full_bar[stg]);
-                    if (need_n) bulk_g2s(cst + SWMAX, a.b.coef[C_N] + row + i0s, cb, &full_bar[stg]);
+                    if (need_n && !CWN) bulk_g2s(cst + SWMAX, a.b.coef[C_N] + row + i0s, cb, &full_bar[stg]);
                     if (centre && XM == XM_ACC) {
                         bulk_g2s(cst + 2 * SWMAX, a.b.xu + row + i0s, cb, &full_bar[stg]);
                         bulk_g2s(cst + 3 * SWMAX, a.b.xv + row + i0s, cb, &full_bar[stg]);
@@ -291,14 +295,27 @@ __global__ void __launch_bounds__(Consumers<PX>::N + 32, 1) k_pcg_pass1_tma(TArg
                     dn = p_from_stage<XM, PX>(st, i0s, tcol, g.nx, lane, beta, alpha_prev,
                                               own ? a.b.xu + xoff : nullptr, own ? a.b.xv + xoff : nullptr);
                     if (!active) { dn.pu = dn.pv = zero; }
-                    if (active && jr < j_b) n_dn = ldv<PX>(st + NHALO * HA + SWMAX + tcol);
+                    if (active && jr < j_b) {
+                        if (CWN) {
+#pragma unroll
+                            for (int k = 0; k < PX; k++) n_dn.v[k] = -1.f;
+                        } else {
+                            n_dn = ldv<PX>(st + NHALO * HA + SWMAX + tcol);
+                        }
+                    }
                     if (own) {
                         // everything the row needs as a centre row goes to registers now, so the stage
                         // returns to the producer at once (bytes in flight = the whole ring)
                         a2_dn = ldv<PX>(st + NHALO * HA + tcol);
-                        const float* Wrow = st + 6 * HA + HALO + tcol;
-                        w_dn = ldv<PX>(Wrow);
-                        wl_dn = (i0 > 0) ? Wrow[-1] : 0.f;     // column i0-1 (never staged at the image edge)
+                        if (CWN) {
+#pragma unroll
+                            for (int k = 0; k < PX; k++) w_dn.v[k] = -1.f;
+                            wl_dn = (i0 > 0) ? -1.f : 0.f;
+                        } else {
+                            const float* Wrow = st + 6 * HA + HALO + tcol;
+                            w_dn = ldv<PX>(Wrow);
+                            wl_dn = (i0 > 0) ? Wrow[-1] : 0.f;     // column i0-1 (never staged at the image edge)
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[stg]);
@@ -390,8 +407,25 @@ bool pcg_pass1_tma_usable(const Geom& g, int nrows)
     return g.nx >= 512 && nrows >= 64 && (g.pitch % 32) == 0;
 }
 
+namespace {
+template <int PX, bool CWN>
+void launch_variant(const TArgs& a, int xm, int grid, size_t smem, cudaStream_t st)
+{
+    static unsigned long long configured = 0;
+    if (first_launch_on_device(&configured)) {
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE, PX, CWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT, PX, CWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC, PX, CWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    const int threads = Consumers<PX>::N + 32;
+    if (xm == XM_NONE)      k_pcg_pass1_tma<XM_NONE, PX, CWN><<<grid, threads, smem, st>>>(a);
+    else if (xm == XM_INIT) k_pcg_pass1_tma<XM_INIT, PX, CWN><<<grid, threads, smem, st>>>(a);
+    else                    k_pcg_pass1_tma<XM_ACC, PX, CWN><<<grid, threads, smem, st>>>(a);
+}
+}  // namespace
+
 void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, int ki, int store_halo,
-                          int sm_count, cudaStream_t st)
+                          int sm_count, cudaStream_t st, int const_wn)
 {
     TArgs a;
     a.b = b; a.g = g; a.ja = ja; a.jb = jb; a.cur = ki & 1; a.store_halo = store_halo;
@@ -424,34 +458,15 @@ void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, in
     int grid = ntasks < sm_count ? ntasks : sm_count;
     if (grid > b.max_partial_blocks) grid = b.max_partial_blocks;
     const size_t smem = (size_t)NSTAGE * STAGE_FLOATS * sizeof(float);
-    static unsigned long long configured = 0;
-    if (first_launch_on_device(&configured)) {
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_NONE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_INIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pcg_pass1_tma<XM_ACC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
     const int xm = ki == 0 ? XM_NONE : (ki == 1 ? XM_INIT : XM_ACC);
-    if (px == 2) {
-        const int threads = SWMAX / 2 + 32;
-        if (xm == XM_NONE)      k_pcg_pass1_tma<XM_NONE, 2><<<grid, threads, smem, st>>>(a);
-        else if (xm == XM_INIT) k_pcg_pass1_tma<XM_INIT, 2><<<grid, threads, smem, st>>>(a);
-        else                    k_pcg_pass1_tma<XM_ACC, 2><<<grid, threads, smem, st>>>(a);
-    } else if (px == 1) {
-        const int threads = Consumers<1>::N + 32;
-        if (xm == XM_NONE)      k_pcg_pass1_tma<XM_NONE, 1><<<grid, threads, smem, st>>>(a);
-        else if (xm == XM_INIT) k_pcg_pass1_tma<XM_INIT, 1><<<grid, threads, smem, st>>>(a);
-        else                    k_pcg_pass1_tma<XM_ACC, 1><<<grid, threads, smem, st>>>(a);
+    if (const_wn) {
+        if (px == 2)      launch_variant<2, true>(a, xm, grid, smem, st);
+        else if (px == 1) launch_variant<1, true>(a, xm, grid, smem, st);
+        else              launch_variant<4, true>(a, xm, grid, smem, st);
     } else {
-        const int threads = SWMAX / 4 + 32;
-        if (xm == XM_NONE)      k_pcg_pass1_tma<XM_NONE, 4><<<grid, threads, smem, st>>>(a);
-        else if (xm == XM_INIT) k_pcg_pass1_tma<XM_INIT, 4><<<grid, threads, smem, st>>>(a);
-        else                    k_pcg_pass1_tma<XM_ACC, 4><<<grid, threads, smem, st>>>(a);
+        if (px == 2)      launch_variant<2, false>(a, xm, grid, smem, st);
+        else if (px == 1) launch_variant<1, false>(a, xm, grid, smem, st);
+        else              launch_variant<4, false>(a, xm, grid, smem, st);
     }
 }
 
