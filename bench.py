@@ -372,6 +372,8 @@ def main():
     ap.add_argument("--taper", type=int, default=None, help="developer: force the limb taper on (1) / off (0)")
     ap.add_argument("--noise-floor", type=float, default=0.0, help="developer: add uniform noise of this amplitude to both frames")
     ap.add_argument("--empty-cache", action="store_true", help="developer: release torch's cached blocks before the first solve")
+    ap.add_argument("--rank-stats", action="store_true",
+                    help="developer (N > 1): add every rank's per-stage CUDA-event times of the profiled step to the line")
     args = ap.parse_args()
     if args.size:
         sx, sy = (int(t) for t in args.size.split("x"))
@@ -545,6 +547,15 @@ def main():
             sys.stdout.flush(); sys.stderr.flush()
             os._exit(0)
 
+    per_rank = None
+    if args.rank_stats and dist:
+        # where the scaling loss sits: per-rank stage times and finest-level pass durations of the profiled step
+        mine = {"rank": rank, "rows": [own0, own1], "pyramid": st.ms_pyramid, "build": st.ms_build,
+                "pcg_pass1": st.ms_pcg_pass1, "pcg_pass2": st.ms_pcg_pass2, "update": st.ms_update, "nav": st.ms_nav,
+                "finest_pass1_ms": st.finest_pass1_ms, "finest_pass2_ms": st.finest_pass2_ms}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+
     if rank != 0:
         del img1, img2, u, v, shorts
         shutdown()
@@ -592,7 +603,9 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
-    if not args.no_cpu_baseline:
+    if per_rank:
+        line["per_rank_stage_ms"] = per_rank
+    if not args.no_cpu_baseline and world == 1:        # the CPU arm is timed at N = 1 only (the other ranks would wait for it)
         line["cpu_baseline"] = run_cpu_port(nx, ny, sector, args.seed)
     if args.ref_cuda:
         try:
