@@ -223,12 +223,37 @@ def reference_arm(args):
             "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": what},
             "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "host_cores_available": os.cpu_count()}
+    if have_ref:
+        line["cpu_stages"] = ref_cpu_stages(args.seed)
     if args.ref_cuda:
         try:
             line["ref_cuda_sm100"] = run_ref_cuda(nx, ny, sector, args.seed)
         except Exception as e:   # no GPU / library absent
             line["ref_cuda_sm100"] = {"unavailable": str(e)[:120]}
     print(json.dumps(line), flush=True)
+
+
+def ref_cpu_stages(seed):
+    """The reference's CPU pyramid / resampling stages (oct_zoom_out = oct_gaussian + oct_bicubic, oct_zoom_in;
+    src/oct_zoom.cc:17,154) on the 500 x 500 texture of BASELINE config 1 and on a 2000 x 2000 one: single-threaded
+    code, best of 3, one host core."""
+    from octane_b200 import synthetic as S
+    from oracle import oracle as O
+    out = {"cores": 1, "unit": "ms", "what": "reference objects (g++ -O3), best of 3"}
+    for n in (500, 2000):
+        img = S.make_pair(n, n, seed)[0].astype("float64")
+        for f in (0.5, 0.25, 0.125):
+            best = min(_timed(lambda: O.ref_zoom_out(img, f)) for _ in range(3))
+            out[f"oct_zoom_out_{n}_f{f}"] = round(best * 1e3, 2)
+        best = min(_timed(lambda: O.ref_zoom_in(img, 2 * n, 2 * n)) for _ in range(3))
+        out[f"oct_zoom_in_{n}_x2"] = round(best * 1e3, 2)
+    return out
+
+
+def _timed(fn):
+    t = time.perf_counter()
+    fn()
+    return time.perf_counter() - t
 
 
 def batch_arm(args):

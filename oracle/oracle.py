@@ -279,6 +279,15 @@ def ref_zoom_out(field, factor):
     return out
 
 
+def ref_zoom_in(field, nxx, nyy):
+    """the reference's CPU prolongation in double (oct_zoom_in, src/oct_zoom.cc:154)"""
+    field = np.ascontiguousarray(field, np.float64)
+    ny, nx = field.shape
+    out = np.zeros((nyy, nxx), np.float64)
+    ref_cpu().ref_zoom_in(field, out, nx, ny, nxx, nyy)
+    return out
+
+
 def srsal(u, v, cth):
     """-srsal bilateral post-smoother restated (src/oct_srsal_cuda.cu:35-71)"""
     u = np.array(u, np.float32, order="C"); v = np.array(v, np.float32, order="C")

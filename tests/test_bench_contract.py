@@ -29,6 +29,9 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    if cb["kind"] == "reference":      # the reference's CPU pyramid stages are timed beside its solver
+        st = d["cpu_stages"]
+        assert st["cores"] == 1 and st["oct_zoom_out_500_f0.5"] > 0 and st["oct_zoom_in_2000_x2"] > st["oct_zoom_in_500_x2"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
