@@ -25,6 +25,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -431,7 +433,7 @@ int fail(const std::string& msg)
 
 }  // namespace
 
-int main(int argc, char* argv[])
+static int run(int argc, char* argv[])
 {
     Flags args;
     std::string f1, f2, f1c, f2c, f1fg, fc21, fc22 = "none", fc31, fc32 = "none", interploc = "./interpolation", outdir = "./";
@@ -705,4 +707,16 @@ int main(int argc, char* argv[])
     octane_ctx_destroy(ctx);
     printf("OCTANE completed, exiting\n");
     return 0;
+}
+
+int main(int argc, char* argv[])
+{
+    try {
+        return run(argc, argv);
+    } catch (const std::bad_alloc&) {          // e.g. a scene larger than host memory
+        fprintf(stderr, "octane: out of host memory\n");
+    } catch (const std::exception& e) {
+        fprintf(stderr, "octane: %s\n", e.what());
+    }
+    return 1;
 }

@@ -2,6 +2,7 @@
 // Replaces the reference's use of netcdf-cxx4 in src/oct_fileread.cc / src/oct_filewrite.cc.
 #include "cdf.h"
 
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -321,6 +322,7 @@ int Reader::open(const std::string& path)
                 const uint32_t id = c.u32();
                 if (id >= dims_.size()) { c.ok = false; break; }
                 v.dimids.push_back((int)id);
+                if (dims_[id].len != 0 && v.nelems > UINT64_MAX / dims_[id].len) { c.ok = false; break; }
                 v.nelems *= dims_[id].len;
             }
             if (!c.ok || !c.att_list(v.atts)) { c.ok = false; break; }
@@ -332,6 +334,17 @@ int Reader::open(const std::string& path)
         }
     } else if (!(tag == 0 && n == 0)) { err_ = path + ": malformed variable list"; return -1; }
     if (!c.ok) { err_ = path + ": truncated or malformed header"; return -1; }
+    // every variable must lie inside the file: callers size their buffers from the header, and a corrupt
+    // dimension would otherwise turn into an absurd allocation long before the short read is noticed
+    if (fseeko(f, 0, SEEK_END) != 0) { err_ = path + ": seek failed"; return -1; }
+    const uint64_t fsize = (uint64_t)ftello(f);
+    for (auto& v : vars_) {
+        const uint64_t es = type_size(v.type);
+        if (v.begin > fsize || v.nelems > (fsize - v.begin) / es) {
+            err_ = path + ": variable " + v.name + " extends beyond the end of the file (truncated or corrupt)";
+            return -1;
+        }
+    }
     return 0;
 }
 

@@ -130,6 +130,35 @@ def test_reader_rejects_what_it_cannot_read(tmp_path):
     assert r.returncode == 1 and "-srsal needs cloud-top heights" in r.stderr
 
 
+def test_reader_survives_corrupt_headers(tmp_path):
+    """truncated files and headers with absurd counts end in an error message and exit code 1, never in an
+    abort: the reader checks every variable's extent against the file size before anybody allocates"""
+    import random
+    tmp = str(tmp_path)
+    d = _pair_files(tmp, nx=48, ny=40)
+    good = open(d["f1"], "rb").read()
+    rng = random.Random(5)
+    bad = os.path.join(tmp, "bad.nc")
+    seen = set()
+    for it in range(60):
+        b = bytearray(good)
+        mode = it % 4
+        if mode == 0:
+            b = b[:rng.randrange(4, len(b))]
+        else:
+            k = rng.randrange(0, 1400 // 4) * 4
+            b[k:k + 4] = {1: bytes([0x7f, 0xff, 0xff, rng.randrange(256)]), 2: b"\xff\xff\xff\xff",
+                          3: bytes(rng.randrange(256) for _ in range(4))}[mode]
+        open(bad, "wb").write(bytes(b))
+        r = run("-i1", bad, "-i2", d["f2"], "-o", tmp + "/", "-dry_run", check=False)
+        assert r.returncode in (0, 1), (it, mode, r.returncode, r.stderr[-300:])
+        seen.add(r.returncode)
+    assert 1 in seen
+    open(bad, "wb").write(good[:len(good) - 100])                       # the last variable is cut short
+    r = run("-i1", bad, "-i2", d["f2"], "-o", tmp + "/", "-dry_run", check=False)
+    assert r.returncode == 1 and "extends beyond the end of the file" in r.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["default", "pd_cth", "firstguess", "cth_coarse_nn", "two_channels", "cth_fine_srsal",
                                   "channel2_fine"])
