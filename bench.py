@@ -233,6 +233,27 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def ref_cuda_child(args):
+    """run_ref_cuda in a child process with a time limit; any failure becomes {"unavailable": why}"""
+    import subprocess
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_cuda.so")):
+        return {"unavailable": "oracle/_ref/libref_cuda.so not built"}
+    try:
+        cmd = [sys.executable, os.path.abspath(__file__), "--ref-cuda-only", "--workload", args.workload, "--seed", str(args.seed)]
+        if args.size:
+            cmd += ["--size", args.size]
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(k, None)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=env)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"unavailable": ("exit %d: " % r.returncode) + (r.stderr.strip().splitlines() or r.stdout.strip().splitlines() or ["no output"])[-1][:160]}
+        return json.loads(lines[-1])
+    except Exception as e:      # timeout, unparsable output, ...
+        return {"unavailable": str(e)[:160]}
+
+
 def ref_cpu_stages(seed):
     """The reference's CPU pyramid / resampling stages (oct_zoom_out = oct_gaussian + oct_bicubic, oct_zoom_in;
     src/oct_zoom.cc:17,154) on the 500 x 500 texture of BASELINE config 1 and on a 2000 x 2000 one: single-threaded
@@ -392,6 +413,7 @@ def main():
     ap.add_argument("--ref-size", type=int, default=1000, help="crop edge of the --impl reference sample")
     ap.add_argument("--ref-cuda", action="store_true", help="also time the reference CUDA build (sm_100 recompile)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-cuda-only", action="store_true", help=argparse.SUPPRESS)   # child process of the baseline leg
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--max-disp", type=int, default=64)
     ap.add_argument("--taper", type=int, default=None, help="developer: force the limb taper on (1) / off (0)")
@@ -404,6 +426,10 @@ def main():
         sx, sy = (int(t) for t in args.size.split("x"))
         WORKLOADS["custom"] = (sx, sy, "conus_0.5km", False)
         args.workload = "custom"
+    if args.ref_cuda_only:
+        nx_, ny_, sector_, _ = WORKLOADS[args.workload]
+        print(json.dumps(run_ref_cuda(nx_, ny_, sector_, args.seed)), flush=True)
+        return
     if args.impl == "reference":
         if args.workload == "batch64":
             args.workload = "meso500"
@@ -632,6 +658,9 @@ def main():
         line["per_rank_stage_ms"] = per_rank
     if not args.no_cpu_baseline and world == 1:        # the CPU arm is timed at N = 1 only (the other ranks would wait for it)
         line["cpu_baseline"] = run_cpu_port(nx, ny, sector, args.seed)
+        # the second baseline BASELINE.json names: the reference's own CUDA build recompiled for sm_100 (oracle/_ref),
+        # on a 2000 x 2000 crop, in a child process (the reference exit()s on errors and leaks device memory)
+        line["cpu_baseline"]["ref_cuda_sm100"] = ref_cuda_child(args)
     if args.ref_cuda:
         try:
             line["ref_cuda_sm100"] = run_ref_cuda(nx, ny, sector, args.seed)
