@@ -216,3 +216,44 @@ def test_plans_that_cannot_run_are_refused_on_the_host():
     assert ws(20, 20) == 0 and b"smaller than 4 pixels" in L.octane_last_error()      # 20 * 0.125 = 3 (rounded)
     assert ws(64, 64, 4) == 0 and ws(64, 64, alpha=0.0) == 0 and ws(64, 64, scaleF=1.0) == 0
     assert ws(64, 64, kiters=4, liters=30) == 0                                        # more than OCTANE_MAX_SOLVES solves
+
+
+def test_band_plan_properties_over_random_scenes():
+    """randomised scenes, world sizes, pyramid depths and displacement bounds: either the plan is refused (a band
+    thinner than its halo, a level smaller than 4 pixels) or the bands tile the scene and every rank's input rows
+    cover what its coarsest level reads -- blur radius R_k at full resolution around (own rows +- warp halo) / factor"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(nx=st.integers(64, 4000), ny=st.integers(64, 30000), world=st.integers(1, 8), kiters=st.integers(1, 5),
+           max_disp=st.integers(0, 96))
+    def check(nx, ny, world, kiters, max_disp):
+        p = ob.default_params(kiters=kiters, max_disp=max_disp)
+        plans = []
+        try:
+            for r in range(world):
+                plans.append(ob.band_plan(nx, ny, p, r, world))
+        except ob.OctaneError as e:
+            assert e.code == -2                      # refused for every rank alike or not at all is checked below
+            return
+        prev = 0
+        for r, (own0, own1, in0, in1) in enumerate(plans):
+            assert own0 == prev and own1 > own0 and 0 <= in0 <= own0 and own1 <= in1 <= ny
+            prev = own1
+            if world == 1:
+                assert (in0, in1) == (0, ny)
+                continue
+            # finest level: warp halo ceil(max_disp) + 3 rows and 4 more for the second derivatives
+            need = max_disp + 7
+            assert own0 - in0 >= min(need, own0) and in1 - own1 >= min(need, ny - own1)
+            for k in range(kiters - 1):              # coarser levels read full-resolution rows through the blur
+                f = 0.5 ** (kiters - 1 - k)
+                yk = int(ny * f + 0.5)
+                o0, o1 = r * yk // world, (r + 1) * yk // world
+                H = max(int(np.ceil(max_disp * f)) + 7, 4)
+                lo, hi = max(o0 - H, 0), min(o1 + H, yk)
+                R = max(5, int(2 * np.float32(1.0 / np.sqrt(2.0 * f))))
+                assert in0 <= max(int(lo / f) - R, 0) and in1 >= min(int((hi - 1) / f) + R, ny)
+        assert prev == ny
+
+    check()
