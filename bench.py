@@ -155,8 +155,72 @@ def run_ref_cuda(nx, ny, sector, seed, size=2000):
         L.ref_optical_flow(i1, i2, None, sx, sy, C.byref(nav), 0.0, dt, C.byref(rp), up, vp, *outs, None, C.byref(dT))
         sec = time.perf_counter() - t
         best = sec if best is None else min(best, sec)
-    return {"value": sx * sy / best / 1e6, "unit": "Mpix/s", "sample": f"{sx}x{sy} centre crop, best of 2, whole oct_optical_flow() "
-            "call (managed-memory migration and host loops included)", "seconds": best, "host_threads": 1}
+    res = {"value": sx * sy / best / 1e6, "unit": "Mpix/s", "sample": f"{sx}x{sy} centre crop, best of 2, whole oct_optical_flow() "
+           "call (managed-memory migration and host loops included)", "seconds": best, "host_threads": 1}
+    # the same crop through this repo's dispatcher (host buffers in and out, like the reference's call): its rate, and
+    # the difference between the two results -- the reference's output is a parity check here, not only a timing
+    try:
+        import octane_b200 as ob
+        ctx = ob.Context(0)
+        onav = ob.goes_nav(xs, ys, xo, yo, minX=c0, minY=r0)
+        ours = None
+        obest = None
+        for _ in range(2):
+            t = time.perf_counter()
+            ours = ctx.oct_optical_flow(i1, i2, onav, 0.0, dt, ob.default_params())
+            sec = time.perf_counter() - t
+            obest = sec if obest is None else min(obest, sec)
+        ctx.close()
+        du, dv = np.abs(ours["uPix"] - up), np.abs(ours["vPix"] - vp)
+        dU = np.abs(ours["uVal"].astype(np.int32) - outs[0]); dV = np.abs(ours["vVal"].astype(np.int32) - outs[1])
+        res["ours_same_crop"] = {"value": sx * sy / obest / 1e6, "unit": "Mpix/s", "seconds": obest,
+                                 "api": "octane_optical_flow (pageable host buffers, best of 2)"}
+        res["delta_vs_ours"] = {"mean_abs_du_px": float(du.mean()), "mean_abs_dv_px": float(dv.mean()),
+                                "max_abs_du_px": float(du.max()), "max_abs_dv_px": float(dv.max()),
+                                "max_abs_dU_counts": int(dU.max()), "max_abs_dV_counts": int(dV.max()),
+                                "frac_U_or_V_differs": float(((dU > 0) | (dV > 0)).mean()),
+                                "within_gates": bool(max(du.mean(), dv.mean()) <= 1e-3 and max(du.max(), dv.max()) <= 1e-2)}
+    except Exception as e:
+        res["delta_vs_ours"] = {"unavailable": str(e)[:160]}
+    return res
+
+
+DIGEST_STRIDE = 64
+
+
+def flow_check(u, v, own0, nx, ny, workload, dist, write):
+    """In-run result check: a strided sample (every 64th row and column) of the flow this run produced, gathered
+    over the ranks and compared with the digest a single-GPU run of the same workload stored under
+    tests/golden/digest_<workload>.npz (`--write-digest`, N = 1).  Collective: every rank calls it."""
+    import numpy as np
+    import torch
+    s = DIGEST_STRIDE
+    rows = [j for j in range(own0, own0 + u.shape[0]) if j % s == 0]
+    idx = torch.tensor([j - own0 for j in rows], device=u.device, dtype=torch.long)
+    mine = (rows, u.index_select(0, idx)[:, ::s].cpu().numpy(), v.index_select(0, idx)[:, ::s].cpu().numpy())
+    parts = [mine]
+    if dist:
+        parts = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+        dist.gather_object(mine, parts, dst=0)
+        if dist.get_rank() != 0:
+            return None
+    parts.sort(key=lambda t: t[0][0] if t[0] else 1 << 30)
+    us = np.concatenate([t[1] for t in parts if t[0]]); vs = np.concatenate([t[2] for t in parts if t[0]])
+    path = os.path.join(ROOT, "tests", "golden", f"digest_{workload}.npz")
+    if write:
+        np.savez_compressed(path, us=us, vs=vs, stride=np.int32(s), nx=np.int32(nx), ny=np.int32(ny))
+        return {"digest": os.path.relpath(path, ROOT), "written": True, "samples": int(us.size)}
+    if not os.path.exists(path):
+        return {"digest": None, "note": "no stored single-GPU digest for this workload"}
+    d = np.load(path)
+    if d["us"].shape != us.shape:
+        return {"digest": os.path.relpath(path, ROOT), "note": "digest shape differs"}
+    du, dv = np.abs(us - d["us"]), np.abs(vs - d["vs"])
+    return {"digest": os.path.relpath(path, ROOT), "what": "strided sample of u, v against the stored single-GPU result",
+            "samples": int(us.size), "max_abs_du": float(du.max()), "max_abs_dv": float(dv.max()),
+            "mean_abs_du": float(du.mean()), "mean_abs_dv": float(dv.mean()),
+            "finite": bool(np.isfinite(us).all() and np.isfinite(vs).all()),
+            "within_gates": bool(max(du.mean(), dv.mean()) <= 1e-3 and max(du.max(), dv.max()) <= 1e-2)}
 
 
 def reference_arm(args):
@@ -209,7 +273,7 @@ def reference_arm(args):
         cores = os.cpu_count()
         sample = f"{i1.shape[1]}x{i1.shape[0]} centre crop"
     torch.set_num_threads(1)
-    for _ in range(args.warmup if args.warmup < 1 else 1):
+    for _ in range(args.warmup):
         fn()
     t = time.perf_counter()
     for _ in range(args.steps):
@@ -217,9 +281,11 @@ def reference_arm(args):
     sec = (time.perf_counter() - t) / args.steps
     v = n / sec / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpix/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload} {nx}x{ny}", "sample": sample},
+            "config": {"workload": f"{args.workload} {nx}x{ny}" + (", patch-match solver (-sosm): the reference's only CPU flow path, "
+                                   "a different and cheaper algorithm than the variational solve" if have_ref else ""),
+                       "sample": sample, "same_algorithm": not have_ref},
             "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": what},
             "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "host_cores_available": os.cpu_count()}
@@ -419,6 +485,8 @@ def main():
     ap.add_argument("--taper", type=int, default=None, help="developer: force the limb taper on (1) / off (0)")
     ap.add_argument("--noise-floor", type=float, default=0.0, help="developer: add uniform noise of this amplitude to both frames")
     ap.add_argument("--empty-cache", action="store_true", help="developer: release torch's cached blocks before the first solve")
+    ap.add_argument("--write-digest", action="store_true",
+                    help="N = 1: store the strided sample of this run's flow that later runs (any N) are checked against")
     ap.add_argument("--rank-stats", action="store_true",
                     help="developer (N > 1): add every rank's per-stage CUDA-event times of the profiled step to the line")
     args = ap.parse_args()
@@ -582,6 +650,9 @@ def main():
         return res
 
 
+    # the flow of the last timed step, checked against the stored single-GPU digest (every rank contributes its rows)
+    check = flow_check(u, v, own0, nx, ny, args.workload, dist, args.write_digest and world == 1)
+
     e2e = None if args.no_e2e else run_e2e()
     torch.cuda.synchronize()
 
@@ -654,6 +725,8 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if check:
+        line["check"] = check
     if per_rank:
         line["per_rank_stage_ms"] = per_rank
     if not args.no_cpu_baseline and world == 1:        # the CPU arm is timed at N = 1 only (the other ranks would wait for it)
@@ -661,6 +734,7 @@ def main():
         # the second baseline BASELINE.json names: the reference's own CUDA build recompiled for sm_100 (oracle/_ref),
         # on a 2000 x 2000 crop, in a child process (the reference exit()s on errors and leaks device memory)
         line["cpu_baseline"]["ref_cuda_sm100"] = ref_cuda_child(args)
+        line["ref_cuda_sm100"] = line["cpu_baseline"]["ref_cuda_sm100"]      # same record at top level
     if args.ref_cuda:
         try:
             line["ref_cuda_sm100"] = run_ref_cuda(nx, ny, sector, args.seed)

@@ -31,8 +31,23 @@ def ctx():
 
 
 def load_golden(name):
+    """tests/golden/<name>.npz; OCTANE_GOLDEN_EXTRA names a second directory (fixtures generated earlier in the
+    same GPU call, before they are committed)"""
     import numpy as np
-    path = os.path.join(GOLDEN, name + ".npz")
-    if not os.path.exists(path):
-        pytest.skip(f"fixture {name}.npz not generated yet (tests/golden/make_golden.py)")
-    return dict(np.load(path))
+    dirs = [GOLDEN] + ([os.environ["OCTANE_GOLDEN_EXTRA"]] if os.environ.get("OCTANE_GOLDEN_EXTRA") else [])
+    for d in dirs:
+        path = os.path.join(d, name + ".npz")
+        if os.path.exists(path):
+            return dict(np.load(path))
+    pytest.skip(f"fixture {name}.npz not generated yet (tests/golden/make_golden*.py)")
+
+
+def parity_report(test, **numbers):
+    """append one line of measured differences to gpurun_out/parity_report.jsonl (when that directory exists):
+    the figures DESIGN.md quotes come from there"""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+        f.write(json.dumps(dict(test=test, **{k: (float(v) if hasattr(v, "__float__") else v) for k, v in numbers.items()})) + "\n")

@@ -215,3 +215,54 @@ def srsal_inputs(c):
         cth[:, : nx // 5] += 40.0                                                          # a low step (partial weight)
         cth += (5.0 * rng.standard_normal((ny, nx))).astype(np.float32)
     return u, v, cth
+
+
+# ---- the benchmarked configurations (BASELINE.json configs 2-4) -----------------------------------
+# Large enough for the TMA-fed PCG kernels (nx >= 512).  The reference's own sm_100 build is valid up to
+# ~178 Mpix (int CSR offsets, src/oct_variational_optical_flow.cu:1222,1293), so the mesoscale sector, CONUS
+# and 2048^2 crops of the tapered full-disk scene all have reference outputs; the fixtures keep a strided
+# sample of u, v (`stride`), one full-resolution block and global statistics.  Inputs are regenerated at
+# test time on the CPU (`S.make_pair_torch(..., "cpu")`), never stored.
+FULLDISK = (21696, 21696)
+HEADLINE = {
+    "ref_1024x768": dict(kind="scene", nx=1024, ny=768, seed=21, stride=3, runs=2),
+    "ref_meso_2000": dict(kind="scene", nx=2000, ny=2000, seed=2, stride=5, runs=2),        # config 2
+    "ref_conus": dict(kind="scene", nx=10000, ny=6000, seed=4, stride=16, runs=1),          # config 3
+    # config 4: crops of the tapered full-disk scene (seed 4, the bench's scene)
+    "ref_fd_centre": dict(kind="fdcrop", x0=9824, y0=9824, size=2048, seed=4, stride=8, runs=2),
+    # the limb on the equator: disk, the taper band x^2+y^2 in [0.021, 0.0212) and space (all-zero columns)
+    "ref_fd_limb": dict(kind="fdcrop", x0=19648, y0=9824, size=2048, seed=4, stride=8, runs=2),
+    # towards the corner: space (zeros) in the upper left, the taper band on the diagonal, disk below it
+    "ref_fd_corner": dict(kind="fdcrop", x0=2600, y0=2600, size=2048, seed=4, stride=8, runs=2),
+}
+BLOCK = 128      # edge of the full-resolution block kept in a headline fixture (at the scene centre)
+
+
+def headline_inputs(c):
+    """(img1, img2) float32 numpy arrays of a HEADLINE case, generated on the CPU"""
+    if c["kind"] == "scene":
+        a, b = S.make_pair_torch(c["nx"], c["ny"], c["seed"], "cpu")
+        return a.numpy(), b.numpy()
+    nx, ny = FULLDISK
+    x0, y0, n = c["x0"], c["y0"], c["size"]
+    a, b = S.make_pair_torch(nx, ny, c["seed"], "cpu", limb_taper=True, rows=(y0, y0 + n))
+    return a[:, x0:x0 + n].contiguous().numpy(), b[:, x0:x0 + n].contiguous().numpy()
+
+
+def headline_digest(u, v, stride):
+    """what a headline fixture keeps of a flow field: strided sample, centre block, float64 statistics"""
+    ny, nx = u.shape
+    by, bx = max(0, ny // 2 - BLOCK // 2), max(0, nx // 2 - BLOCK // 2)
+    return dict(us=np.ascontiguousarray(u[::stride, ::stride]), vs=np.ascontiguousarray(v[::stride, ::stride]),
+                ub=np.ascontiguousarray(u[by:by + BLOCK, bx:bx + BLOCK]), vb=np.ascontiguousarray(v[by:by + BLOCK, bx:bx + BLOCK]),
+                stats=np.array([np.abs(u, dtype=np.float64).mean(), np.abs(v, dtype=np.float64).mean(),
+                                float(np.abs(u).max()), float(np.abs(v).max()),
+                                u.astype(np.float64).sum(), v.astype(np.float64).sum()]))
+
+
+def input_hash(*arrays):
+    import hashlib
+    h = hashlib.sha1()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
