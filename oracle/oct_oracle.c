@@ -391,6 +391,22 @@ static float dot2(const float *au, const float *av, const float *bu, const float
     return (float)t;
 }
 
+static double dot2d(const float *au, const float *av, const float *bu, const float *bv,
+                    int xi, int yi, double *rowsum)
+{
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < yi; j++) {
+        double s = 0;
+        const size_t o = (size_t)j * xi;
+        for (int i = 0; i < xi; i++)
+            s += (double)(au[o + i] * bu[o + i]) + (double)(av[o + i] * bv[o + i]);
+        rowsum[j] = s;
+    }
+    double t = 0;
+    for (int j = 0; j < yi; j++) t += rowsum[j];
+    return t;
+}
+
 /* Jacobi-PCG, :1105-1182.  x starts at 0, so r0 = b (:1105-1113).
  * work: 8 planes of xi*yi floats.  Returns iterations executed. */
 int oracle_pcg(const float *coef, float *bu, float *bv, float *xu, float *xv,
@@ -436,6 +452,66 @@ int oracle_pcg(const float *coef, float *bu, float *bv, float *xu, float *xv,
             rv[i] = fmaf(nalpha, qv[i], bv[i]);
         }
         residc = dot2(ru, rv, ru, rv, xi, yi, rowsum);                /* :1178 */
+        ki++;
+    }
+    free(qu); free(rowsum);
+    return ki;
+}
+
+/* ---- model of the product's single-reduction PCG (octane_b200/csrc/pcg_fused.cu) ------------------
+ * NOT a restatement of the reference: the same Krylov iterate as oracle_pcg in exact arithmetic, computed with the
+ * merged-reduction recurrences (w = A z, q = w + beta q instead of q = A p; one dot-product phase per iteration:
+ * r.z, r.r, z.w, z.q, p.w, p.q), scalars in double, vectors in float.  It exists so that the distance between
+ * the two recurrences can be measured on the CPU (tests/test_oracle_golden.py) and so that the CUDA kernel has a
+ * model with the same operation order.  Selected with oracle_set_solver(1); the default (0) is the reference's
+ * recurrence, which every parity gate is judged against. */
+static int g_solver = 0;
+void oracle_set_solver(int s) { g_solver = s; }
+
+int oracle_pcg_merged(const float *coef, float *bu, float *bv, float *xu, float *xv,
+                      int xi, int yi, int iters, float tol, float *work)
+{
+    const size_t n = (size_t)xi * yi;
+    const float *A1 = coef, *A4 = coef + 2 * n;
+    float *mu = work, *mv = work + n, *zu = work + 2 * n, *zv = work + 3 * n;
+    float *pu = work + 4 * n, *pv = work + 5 * n, *wu = work + 6 * n, *wv = work + 7 * n;
+    float *qu = (float *)calloc(2 * n, sizeof(float)), *qv = qu + n;
+    double *rowsum = (double *)malloc(sizeof(double) * yi);
+    float *ru = bu, *rv = bv;                               /* r0 = b (x0 = 0), updated in place */
+    for (size_t i = 0; i < n; i++) {
+        xu[i] = 0; xv[i] = 0; pu[i] = 0; pv[i] = 0;
+        mu[i] = (float)(1. / A1[i]);
+        mv[i] = (float)(1. / A4[i]);
+        zu[i] = mu[i] * ru[i]; zv[i] = mv[i] * rv[i];
+    }
+    float rr = dot2(ru, rv, ru, rv, xi, yi, rowsum);
+    int ki = 0;
+    if (!(rr > tol) || iters <= 0) { free(qu); free(rowsum); return 0; }
+    oracle_apply(coef, zu, zv, xi, yi, wu, wv);
+    double gamma = dot2d(ru, rv, zu, zv, xi, yi, rowsum);
+    double pAp = dot2d(wu, wv, zu, zv, xi, yi, rowsum);     /* p0 = z0: p0.Ap0 = z0.w0 */
+    double alpha = gamma / pAp, beta = 0.0;
+    while ((rr > tol) && (ki < iters)) {
+        const float af = (float)alpha, bf = (float)beta, naf = -af;
+        for (size_t i = 0; i < n; i++) {
+            pu[i] = fmaf(bf, pu[i], zu[i]);  pv[i] = fmaf(bf, pv[i], zv[i]);      /* p = z + beta p */
+            qu[i] = fmaf(bf, qu[i], wu[i]);  qv[i] = fmaf(bf, qv[i], wv[i]);      /* q = w + beta q  (= A p) */
+            xu[i] = fmaf(af, pu[i], xu[i]);  xv[i] = fmaf(af, pv[i], xv[i]);
+            ru[i] = fmaf(naf, qu[i], ru[i]); rv[i] = fmaf(naf, qv[i], rv[i]);
+            zu[i] = mu[i] * ru[i];           zv[i] = mv[i] * rv[i];
+        }
+        oracle_apply(coef, zu, zv, xi, yi, wu, wv);
+        /* one reduction phase: everything the next iteration's scalars need.  The boundary-merged matrix is NOT
+         * symmetric (a7(0,j) = 2 W, a5(1,j) = W), so p.Ap of the next direction p' = z + beta' p is expanded without
+         * assuming symmetry: p'.Ap' = z.w + beta' (z.q + p.w) + beta'^2 p.q */
+        const double gnew = dot2d(ru, rv, zu, zv, xi, yi, rowsum);
+        const double zw = dot2d(zu, zv, wu, wv, xi, yi, rowsum), zq = dot2d(zu, zv, qu, qv, xi, yi, rowsum);
+        const double pw = dot2d(pu, pv, wu, wv, xi, yi, rowsum), pq = dot2d(pu, pv, qu, qv, xi, yi, rowsum);
+        rr = dot2(ru, rv, ru, rv, xi, yi, rowsum);
+        beta = gnew / gamma;
+        pAp = zw + beta * (zq + pw) + beta * beta * pq;
+        alpha = gnew / pAp;
+        gamma = gnew;
         ki++;
     }
     free(qu); free(rowsum);
@@ -496,7 +572,8 @@ int oracle_variational_flow(const float *img1, const float *img2, int nx, int ny
             for (int l = 0; l < liters; l++) {
                 oracle_build(uval, vval, uvalt, vvalt, geo1, g1x, g1y, geo2, g2x, g2y, g2xx, g2xy, g2yy,
                              xi, yi, nc, alpha, lambdadalpha, lambdac, gnc, p->dozim != 0, coef, bu, bv);
-                int its = oracle_pcg(coef, bu, bv, xu, xv, xi, yi, iters, tol, work);
+                int its = g_solver ? oracle_pcg_merged(coef, bu, bv, xu, xv, xi, yi, iters, tol, work)
+                                   : oracle_pcg(coef, bu, bv, xu, xv, xi, yi, iters, tol, work);
                 if (cg_its) cg_its[solve] = its;
                 solve++;
                 for (size_t i = 0; i < n; i++) { uval[i] = uval[i] + xu[i]; vval[i] = vval[i] + xv[i]; }  /* :1185-1195 */
