@@ -482,6 +482,8 @@ def main():
     ap.add_argument("--ref-cuda-only", action="store_true", help=argparse.SUPPRESS)   # child process of the baseline leg
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--max-disp", type=int, default=64)
+    ap.add_argument("--solver", type=int, default=1, choices=[0, 1],
+                    help="PCG kernels of the large levels: 1 merged reduction (default), 0 the reference's loop literally")
     ap.add_argument("--taper", type=int, default=None, help="developer: force the limb taper on (1) / off (0)")
     ap.add_argument("--noise-floor", type=float, default=0.0, help="developer: add uniform noise of this amplitude to both frames")
     ap.add_argument("--empty-cache", action="store_true", help="developer: release torch's cached blocks before the first solve")
@@ -534,6 +536,7 @@ def main():
     ctx = ob.Context(local)
     if os.environ.get("OCTANE_NO_GRAPHS"):      # profiling under ncu: plain launches
         ctx.set_graphs(False)
+    ctx.set_solver(args.solver)
     if world > 1:
         ids = [ob.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -686,22 +689,29 @@ def main():
     # ---- roofline of the dominant kernel (finest-level PCG passes, timed live above)
     peak, peak_src = peaks()
     its = list(st.cg_iterations[:st.n_solves])
-    b1 = pass1_bytes(its[-3 * p.liters:])          # the finest level's solves
+    fused = int(st.pcg_solver) == 1
+    # algorithmic bytes per pixel of the launches the average duration was taken over (the library counts them per
+    # launch: which vectors exist yet, whether the constant W / N planes are skipped)
+    b1 = float(st.finest_pass1_bytes_per_px) or pass1_bytes(its[-3 * p.liters:])
     k1 = b1 * st.finest_pixels / (st.finest_pass1_ms * 1e-3) / 1e9 if st.finest_pass1_ms > 0 else 0.0
     k2 = B_PASS2 * st.finest_pixels / (st.finest_pass2_ms * 1e-3) / 1e9 if st.finest_pass2_ms > 0 else 0.0
-    dom = "pcg_pass2" if st.ms_pcg_pass2 >= st.ms_pcg_pass1 else "pcg_pass1"
+    if fused:
+        dom = "pcg_fused"          # one kernel per iteration: the library times it in the pass-1 slot
+    else:
+        dom = "pcg_pass2" if st.ms_pcg_pass2 >= st.ms_pcg_pass1 else "pcg_pass1"
     ach = k2 if dom == "pcg_pass2" else k1
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dom)     # bytes per launch (ncu, see the file's note)
+            # bytes per launch from one ncu --set full capture, keyed by workload AND rank count (see the file's note)
+            traffic = json.load(f).get(args.workload, {}).get(f"n{world}", {}).get(dom)
     except Exception:
         pass
     line = {
         "metric": METRIC, "value": mpix / (ms_step / 1e3), "unit": "Mpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload} {nx}x{ny} band-2-like pair, {sector}", "nc": 1,
+        "config": {"workload": f"{args.workload} {nx}x{ny} band-2-like pair, {sector}", "nc": 1, "solver": args.solver,
                    "alpha": p.alpha, "lambda": p.lambda_, "kiters": p.kiters, "liters": p.liters, "cgiters": p.cgiters,
                    "parallelism": f"row bands x{world}" if world > 1 else "single GPU",
                    "l2": "inputs and every level-3 plane are larger than L2 (no flush needed)" if nx * ny * 4 > 130e6
@@ -713,11 +723,14 @@ def main():
                      "peak_source": peak_src,
                      "bytes_per_pixel_per_launch": B_PASS2 if dom == "pcg_pass2" else b1,
                      "pixels_per_launch": int(st.finest_pixels),
-                     "pass1": {"GB/s": k1, "avg_ms": st.finest_pass1_ms}, "pass2": {"GB/s": k2, "avg_ms": st.finest_pass2_ms},
+                     ("fused" if fused else "pass1"): {"GB/s": k1, "avg_ms": st.finest_pass1_ms, "bytes_per_pixel": b1},
+                     "pass2": {"GB/s": k2, "avg_ms": st.finest_pass2_ms} if not fused else None,
+                     "solver": "merged reduction: one launch per PCG iteration" if fused else "two launches per PCG iteration",
                      "whole_step": {"algorithmic_GB": st.algorithmic_bytes * world / 1e9,
                                     "GB/s_per_gpu": st.algorithmic_bytes / (ms_step * 1e-3) / 1e9,
                                     "frac": st.algorithmic_bytes / (ms_step * 1e-3) / 1e9 / peak}},
-        "stage_ms": {"pyramid": st.ms_pyramid, "build": st.ms_build, "pcg_pass1": st.ms_pcg_pass1,
+        "stage_ms": {"pyramid": st.ms_pyramid, "build": st.ms_build,
+                     ("pcg_fused_and_small_pass1" if fused else "pcg_pass1"): st.ms_pcg_pass1,
                      "pcg_pass2": st.ms_pcg_pass2, "update": st.ms_update, "nav": st.ms_nav,
                      "profiled_step_ms": ms_prof,
                      "note": "from one extra step with per-launch events; PCG passes timed at the finest level only"},

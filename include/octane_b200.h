@@ -56,7 +56,8 @@
 extern "C" {
 #endif
 
-#define OCTANE_ABI_VERSION 2   /* 2: octane_params.dosrsal appended; zoom-out and srsal entry points */
+#define OCTANE_ABI_VERSION 3   /* 2: octane_params.dosrsal appended; zoom-out and srsal entry points
+                                  3: octane_ctx_set_solver; octane_stats.pcg_solver, finest_pass1_bytes_per_px appended */
 
 enum {
     OCTANE_OK = 0,
@@ -134,6 +135,9 @@ typedef struct octane_stats {
     long long n_pcg_pass1, n_pcg_pass2;   /* launches that did work (not early-exited) */
     double finest_pass1_ms, finest_pass2_ms;   /* average per working launch, finest level */
     long long finest_pixels;              /* pixels one finest-level launch covers on this rank */
+    int pcg_solver;                       /* kernels the finest level ran: 1 merged reduction (one launch per iteration,
+                                             timed as "pass1", no pass 2), 0 the two-pass kernels */
+    double finest_pass1_bytes_per_px;     /* algorithmic bytes per pixel, averaged over the launches finest_pass1_ms averages */
 } octane_stats;
 
 typedef struct octane_ctx octane_ctx;
@@ -150,6 +154,11 @@ int  octane_ctx_create(octane_ctx** ctx, int device);
 void octane_ctx_destroy(octane_ctx* ctx);
 int  octane_ctx_set_profile(octane_ctx* ctx, int on);      /* per-stage CUDA-event timing */
 int  octane_ctx_set_graphs(octane_ctx* ctx, int on);       /* CUDA-graph the PCG loop (default on) */
+/* PCG kernels of the large levels.  1 (default): the merged form of the reference's recurrence -- one launch and one
+ * reduction phase per iteration, 68-84 B/px; the same Krylov iterate as the reference's loop
+ * (src/oct_variational_optical_flow.cu:1131-1182) up to fp32 rounding (measured: its own run-to-run noise).
+ * 0: that loop literally, two launches per iteration, 100 B/px.  Small levels always run 0. */
+int  octane_ctx_set_solver(octane_ctx* ctx, int solver);
 int  octane_get_stats(octane_ctx* ctx, octane_stats* out);
 int  octane_ctx_synchronize(octane_ctx* ctx);
 void* octane_ctx_stream(octane_ctx* ctx);                  /* the cudaStream_t all work is ordered on */

@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OCTANE_B200_LIB") or os.path.join(HERE, "lib", "liboctane_b200.so")
 
 OCTANE_MAX_SOLVES = 256
+EXPECTED_ABI = 3          # include/octane_b200.h: OCTANE_ABI_VERSION the struct mirrors below were written against
 
 
 class Params(C.Structure):
@@ -52,13 +53,13 @@ class Stats(C.Structure):
                 ("ms_pcg_pass1", C.c_double), ("ms_pcg_pass2", C.c_double), ("ms_update", C.c_double),
                 ("ms_nav", C.c_double), ("n_pcg_pass1", C.c_longlong), ("n_pcg_pass2", C.c_longlong),
                 ("finest_pass1_ms", C.c_double), ("finest_pass2_ms", C.c_double),
-                ("finest_pixels", C.c_longlong)]
+                ("finest_pixels", C.c_longlong), ("pcg_solver", C.c_int), ("finest_pass1_bytes_per_px", C.c_double)]
 
 
 # every symbol include/octane_b200.h declares (tests check the library exports them all)
 EXPORTS = [
     "octane_abi_version", "octane_last_error", "octane_device_count", "octane_params_default",
-    "octane_ctx_create", "octane_ctx_destroy", "octane_ctx_set_profile", "octane_ctx_set_graphs",
+    "octane_ctx_create", "octane_ctx_destroy", "octane_ctx_set_profile", "octane_ctx_set_graphs", "octane_ctx_set_solver",
     "octane_get_stats", "octane_ctx_synchronize", "octane_ctx_stream", "octane_workspace_bytes", "octane_level_dims",
     "octane_variational_flow", "octane_pix2uv", "octane_optical_flow",
     "octane_variational_flow_dev", "octane_pix2uv_dev", "octane_optical_flow_dev",
@@ -82,6 +83,10 @@ def load() -> C.CDLL:
         raise ImportError(f"{LIB_PATH} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(octane_b200 has no fallback path)")
     L = C.CDLL(LIB_PATH)
+    L.octane_abi_version.restype = C.c_int
+    if L.octane_abi_version() != EXPECTED_ABI:
+        # a library and mirror that disagree would read / write past the ctypes structs silently
+        raise ImportError(f"{LIB_PATH} has ABI version {L.octane_abi_version()}, this package mirrors version {EXPECTED_ABI}")
     vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
     PP, NP = C.POINTER(Params), C.POINTER(Nav)
     i, d, f = C.c_int, C.c_double, C.c_float
@@ -95,6 +100,7 @@ def load() -> C.CDLL:
     L.octane_ctx_destroy.restype = None
     L.octane_ctx_set_profile.argtypes = [vp, i]
     L.octane_ctx_set_graphs.argtypes = [vp, i]
+    L.octane_ctx_set_solver.argtypes = [vp, i]
     L.octane_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.octane_ctx_synchronize.argtypes = [vp]
     L.octane_ctx_stream.argtypes = [vp]

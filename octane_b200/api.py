@@ -174,6 +174,10 @@ class Context:
     def set_graphs(self, on: bool):
         self._check(self._L.octane_ctx_set_graphs(self._h, int(on)))
 
+    def set_solver(self, solver: int):
+        """1 (default): merged-reduction PCG kernels on the large levels; 0: the reference's recurrence literally"""
+        self._check(self._L.octane_ctx_set_solver(self._h, int(solver)))
+
     def synchronize(self):
         self._check(self._L.octane_ctx_synchronize(self._h))
 

@@ -297,13 +297,7 @@ void launch_build(const LevelFields& f, const PcgBuffers& b, const Geom& g, int 
                   const BuildParams& bp, int halo_check, cudaStream_t st)
 {
     dim3 grid((g.nx + 31) / 32, (jb - ja + BUILD_ROWS - 1) / BUILD_ROWS), block(32, 8);
-    // developer switch: resident blocks per SM the register allocation aims at (2 -> 128 registers, no spills)
-    static const int occ = getenv("OCTANE_BUILD_OCC") ? atoi(getenv("OCTANE_BUILD_OCC")) : 3;
-#define LAUNCH_BUILD(MODE)                                                                              \
-    do {                                                                                                \
-        if (occ == 2) k_build<MODE, 2><<<grid, block, 0, st>>>(f, b, g, ja, jb, da, db, bp, halo_check); \
-        else          k_build<MODE, 3><<<grid, block, 0, st>>>(f, b, g, ja, jb, da, db, bp, halo_check); \
-    } while (0)
+#define LAUNCH_BUILD(MODE) k_build<MODE, 3><<<grid, block, 0, st>>>(f, b, g, ja, jb, da, db, bp, halo_check)
     if (bp.al1 == 1.0)      LAUNCH_BUILD(GNC_QUADRATIC);
     else if (bp.al1 == 0.0) LAUNCH_BUILD(GNC_ROBUST);
     else                    LAUNCH_BUILD(GNC_BLEND);

@@ -47,6 +47,11 @@ struct PcgScalars {
     int its;        // iterations executed in this solve
     int halo_err;   // banded runs: warp left the local rows
     int comm_err;   // banded runs: a peer's contribution did not arrive in time
+    // merged-reduction solver (pcg_fused.cu): scalar recurrences in double, narrowed once for the vector updates
+    double d_gamma; // r.z of the current residual
+    double d_alpha; // step of the NEXT launch
+    float f_alpha, f_beta;   // what the next launch applies: x += alpha p, p = z + beta p
+    float f_alpha_prev;      // alpha of the launch before (its x term is applied every second launch)
 };
 
 // ---- peer-memory exchange between the row bands (one process per GPU) -----------------------
@@ -60,7 +65,7 @@ struct PcgScalars {
 constexpr int P2P_MAXW = 16;
 enum { P2P_BUILD = 0, P2P_PASS1 = 1, P2P_PASS2 = 2, P2P_NPHASE = 3 };
 struct P2PWindow {
-    double val[P2P_NPHASE][2][P2P_MAXW][2];
+    double val[P2P_NPHASE][2][P2P_MAXW][8];    // up to 8 sums per phase (the merged-reduction solver exchanges 6)
     unsigned seq[P2P_NPHASE][2][P2P_MAXW];
 };
 struct P2P {

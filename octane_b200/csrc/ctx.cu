@@ -69,6 +69,7 @@ struct Level {
     // peer-memory runs: the neighbours' r planes, shifted so that p[g.at(i, j)] with THIS rank's
     // geometry addresses (i, j) in the neighbour's plane (nullptr at the outer edges)
     float *up_ru = nullptr, *up_rv = nullptr, *dn_ru = nullptr, *dn_rv = nullptr;
+    FusedPeers fp = {};      // the same for the merged-reduction solver: both buffers of r and q
 };
 
 struct Plan {
@@ -77,10 +78,14 @@ struct Plan {
     std::vector<Level> lv;
     int in0 = 0, in1 = 0;    // full-res input rows needed (== finest level's local rows)
     size_t P = 0, Pc = 0;    // plane sizes (floats): finest, second finest
+    // only what shapes the workspace, the graphs and the band geometry: a change of pixuv / doCTH / ir / dosrsal /
+    // setdevice (or of struct padding) must not force a re-plan -- in banded runs a re-plan is a collective
     bool same(int nx_, int ny_, int nc_, const octane_params& q, int rank_, int world_) const
     {
         return nx == nx_ && ny == ny_ && nc == nc_ && rank == rank_ && world == world_ &&
-               memcmp(&p, &q, sizeof q) == 0;
+               p.alpha == q.alpha && p.lambda == q.lambda && p.lambdac == q.lambdac && p.scaleF == q.scaleF &&
+               p.kiters == q.kiters && p.liters == q.liters && p.cgiters == q.cgiters && p.dozim == q.dozim &&
+               p.first_guess == q.first_guess && p.max_disp == q.max_disp;
     }
 };
 
@@ -167,9 +172,10 @@ struct octane_ctx {
     cudaStream_t copy_stream = nullptr;   // host-buffer entry points: result copies that overlap the next stage
     cudaEvent_t ev_stage = nullptr;
     bool profile = false, graphs = true;
-    bool use_tma = getenv("OCTANE_NO_TMA") == nullptr;   // developer switch: v1 pass-1 kernel everywhere
-    // experimental (not measured yet): the first GNC stage's solves skip the constant W / N planes in pass 1
-    bool const_wn = getenv("OCTANE_CONST_WN") != nullptr;
+    // PCG kernels of the large levels: 1 = merged recurrence, one launch and one reduction per iteration
+    // (pcg_fused.cu, the default); 0 = the reference's recurrence literally, two launches (pcg_tma.cu + pcg.cu).
+    // Small levels always run the latter (octane_ctx_set_solver).
+    int solver = 1;
     Comm comm;
     // workspace
     char* arena = nullptr;
@@ -211,11 +217,9 @@ size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t arena_layout(const Plan& pl, Buffers* b, char* base)
 {
     size_t off = 0;
-    // developer switch for address-translation experiments: spread the planes over more memory
-    static const size_t pad = getenv("OCTANE_PLANE_PAD_MB") ? (size_t)atol(getenv("OCTANE_PLANE_PAD_MB")) << 20 : 0;
     auto take = [&](size_t nfloats) -> float* {
         float* p = base ? (float*)(base + off) : nullptr;
-        off += align_up(nfloats * sizeof(float)) + pad;
+        off += align_up(nfloats * sizeof(float));
         return p;
     };
     const size_t P = pl.P, Pc = pl.Pc, nc = pl.nc;
@@ -232,6 +236,8 @@ size_t arena_layout(const Plan& pl, Buffers* b, char* base)
     B.pcg.ru = take(P); B.pcg.rv = take(P); B.pcg.xu = take(P); B.pcg.xv = take(P);
     B.pcg.pu[0] = take(P); B.pcg.pu[1] = take(P); B.pcg.pv[0] = take(P); B.pcg.pv[1] = take(P);
     B.pcg.qu = take(P); B.pcg.qv = take(P);
+    B.pcg.q2u = take(P); B.pcg.q2v = take(P);
+    B.pcg.r2u = B.pcg.pu[1]; B.pcg.r2v = B.pcg.pv[1];     // the merged-reduction solver keeps p in pu[0] / pv[0] only
     return off;
 }
 
@@ -303,6 +309,14 @@ int prepare(octane_ctx* c, int nx, int ny, int nc, const octane_params& p)
                 const long long shift = (long long)(pl.lv[k].g.j0 - pn.lv[k].g.j0) * pl.lv[k].g.pitch;
                 if (side == 0) { pl.lv[k].up_ru = bn.pcg.ru + shift; pl.lv[k].up_rv = bn.pcg.rv + shift; }
                 else { pl.lv[k].dn_ru = bn.pcg.ru + shift; pl.lv[k].dn_rv = bn.pcg.rv + shift; }
+                FusedPeers& fp = pl.lv[k].fp;
+                float* rb[2][2] = { { bn.pcg.ru, bn.pcg.rv }, { bn.pcg.r2u, bn.pcg.r2v } };
+                float* qb[2][2] = { { bn.pcg.qu, bn.pcg.qv }, { bn.pcg.q2u, bn.pcg.q2v } };
+                for (int bi = 0; bi < 2; bi++)
+                    for (int ci = 0; ci < 2; ci++) {
+                        (side == 0 ? fp.up_r : fp.dn_r)[bi][ci] = rb[bi][ci] + shift;
+                        (side == 0 ? fp.up_q : fp.dn_q)[bi][ci] = qb[bi][ci] + shift;
+                    }
             }
         }
     }
@@ -386,6 +400,12 @@ int allreduce_pending(octane_ctx* c, int n)
     return OCTANE_OK;
 }
 
+// the merged-reduction kernels serve the levels that are large enough for them, on one GPU or over peer memory
+bool level_fused(const octane_ctx* c, const Level& L)
+{
+    return c->solver == 1 && pcg_fused_usable(L.g, L.own1 - L.own0) && (c->comm.world <= 1 || c->comm.p2p);
+}
+
 // ---- the PCG loop of one solve (:1129-1182), enqueued or captured ----------------------
 int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve, int const_wn)
 {
@@ -393,6 +413,16 @@ int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve, int const_w
     const int iters = c->plan.p.cgiters;
     const bool multi = c->comm.world > 1;
     const bool p2p = multi && c->comm.p2p;
+    if (level_fused(c, L)) {
+        // one launch per iteration (+ one that forms the first alpha); r and q halo rows and the six sums
+        // cross the band boundaries inside the kernel (peer memory)
+        for (int ki = -1; ki < iters; ki++) {
+            Scope s(c, CAT_P1, level, solve, ki);
+            launch_pcg_fused(b, L.g, L.own0, L.own1, ki, L.fp, c->sm_count, c->stream, const_wn);
+            c->launches++;
+        }
+        return OCTANE_OK;
+    }
     // peer-memory runs: pass 2 stores its boundary rows of r straight into the neighbours' halo rows
     // and the last block of each pass sums the dots across the ranks itself (2 launches per iteration,
     // as on one GPU); otherwise NCCL: all-reduce + a scalar kernel after each pass, send/recv of r
@@ -400,7 +430,7 @@ int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve, int const_w
     for (int ki = 0; ki < iters; ki++) {
         {
             Scope s(c, CAT_P1, level, solve, ki);
-            if (c->use_tma && pcg_pass1_tma_usable(L.g, L.own1 - L.own0))
+            if (pcg_pass1_tma_usable(L.g, L.own1 - L.own0))
                 launch_pcg_pass1_tma(b, L.g, L.own0, L.own1, ki, multi, c->sm_count, c->stream, const_wn);
             else
                 launch_pcg_pass1(b, L.g, L.own0, L.own1, ki, multi, c->sm_count, c->stream);
@@ -447,7 +477,8 @@ int run_pcg(octane_ctx* c, const Level& L, int level, int solve, int const_wn)
         c->pcg_graph[slot] = exec;
     }
     CUDA_OK(cudaGraphLaunch(c->pcg_graph[slot], c->stream));
-    c->launches += (long long)c->plan.p.cgiters * ((c->comm.world > 1 && !c->comm.p2p) ? 4 : 2);
+    if (level_fused(c, L)) c->launches += (long long)c->plan.p.cgiters + 1;
+    else c->launches += (long long)c->plan.p.cgiters * ((c->comm.world > 1 && !c->comm.p2p) ? 4 : 2);
     return OCTANE_OK;
 }
 
@@ -520,9 +551,11 @@ int run_levels(octane_ctx* c)
         BuildParams bp;
         bp.alpha = p.alpha; bp.ralpha = 1.0 / p.alpha; bp.lambdadalpha = p.lambda / p.alpha; bp.lambdac = L.lambdac;
         bp.dozim = p.dozim != 0; bp.nchan = nc; bp.tol = 0.0001 * 0.0001;       // :1353
-        // rows to build: owned rows plus one halo row each side (pass 1 rebuilds p there)
+        // rows to build: owned rows plus the halo rows the PCG kernels rebuild z (and p) on -- one each side for the
+        // two-pass kernels, two for the merged-reduction kernel (its second stencil reaches one row further)
+        const bool fused = level_fused(c, L);
         int ba = L.own0, bb = L.own1;
-        if (multi) { if (ba > 0) ba--; if (bb < g.ny) bb++; }
+        if (multi) { const int h = fused ? 2 : 1; ba = ba - h < 0 ? 0 : ba - h; bb = bb + h > g.ny ? g.ny : bb + h; }
         for (int gnc = 0; gnc < 3; gnc++) {                       // :604-608
             bp.al1 = 1. - 0.5 * gnc;
             for (int l = 0; l < p.liters; l++, solve++) {
@@ -535,11 +568,13 @@ int run_levels(octane_ctx* c)
                         launch_finalize(B.pcg, FINALIZE_BUILD, bp.tol, st); c->launches++;
                     }
                 }
-                int rc = run_pcg(c, L, k, solve, (c->const_wn && gnc == 0) ? 1 : 0);
+                // the first GNC stage's systems have W = N = -1 everywhere: those solves do not read the two planes
+                int rc = run_pcg(c, L, k, solve, gnc == 0 ? 1 : 0);
                 if (rc) return rc;
                 {
                     Scope s(c, CAT_UPDATE, k, solve);             // :1185-1195
-                    launch_update_uv(B.u, B.v, B.pcg, g, L.own0, L.own1, c->d_its + solve, c->sm_count, st);
+                    if (fused) launch_update_uv_fused(B.u, B.v, B.pcg, g, L.own0, L.own1, c->d_its + solve, c->sm_count, st);
+                    else launch_update_uv(B.u, B.v, B.pcg, g, L.own0, L.own1, c->d_its + solve, c->sm_count, st);
                     c->launches++;
                     float* planes[2] = { B.u, B.v };
                     rc = exchange_rows(c, L, 2, planes, HALO_UV); if (rc) return rc;
@@ -665,6 +700,17 @@ int pix2uv_dev_rows(octane_ctx* c, const octane_nav* nav, double t1, double t2, 
     return OCTANE_OK;
 }
 
+// algorithmic bytes per pixel of one merged-reduction launch: r, q, p in and out, x in and out
+// every second iteration, the five coefficient planes (three when W = N = -1 is known)
+double fused_bytes(int ki, bool cwn)
+{
+    const double coef = cwn ? 12.0 : 20.0;
+    if (ki < 0) return 8.0 + coef;                       // r + coefficients, nothing written
+    if (ki == 0) return 8.0 + coef + 24.0;               // no p, q of a previous iteration yet
+    if (ki == 1) return 24.0 + coef + 32.0;              // x is started, not read
+    return (ki & 1) ? 32.0 + coef + 32.0 : 24.0 + coef + 24.0;
+}
+
 void collect_stats(octane_ctx* c)
 {
     octane_stats& s = c->stats;
@@ -684,11 +730,21 @@ void collect_stats(octane_ctx* c)
         // (72 B/px), pass 1 (44 / 60 / 68 B/px for iteration 0 / 1 / later), pass 2 (32 B/px)
         // for the iterations actually executed, and the u,v update (32 B/px)
         bytes += Nk * 100.0;
+        const bool fused = level_fused(c, L);
         for (int q = 0; q < 3 * pl.p.liters; q++, solve++) {
             const int n = c->h_its[solve];
             s.cg_iterations[solve] = n;
-            double per = 72.0 + 32.0 * n + (n >= 1 ? 44.0 : 0.0) + (n >= 2 ? 60.0 : 0.0) + (n > 2 ? 68.0 * (n - 2) : 0.0);
-            if (n >= 1) per += 32.0;
+            const bool cwn = q < pl.p.liters;          // first GNC stage: W, N are not read by the large-level kernels
+            double per = 72.0;                          // build
+            if (fused) {
+                per += fused_bytes(-1, cwn);            // the launch that forms the first alpha runs whenever the solve does
+                for (int ki = 0; ki < n; ki++) per += fused_bytes(ki, cwn);
+                if (n >= 1) per += 8.0 + 8.0 + (n >= 2 ? 8.0 : 0.0) + ((n & 1) ? 8.0 : 0.0);     // u, v in and out, x, pending p
+            } else {
+                per += 32.0 * n + (n >= 1 ? 44.0 : 0.0) + (n >= 2 ? 60.0 : 0.0) + (n > 2 ? 68.0 * (n - 2) : 0.0);
+                if (cwn && pcg_pass1_tma_usable(L.g, L.own1 - L.own0)) per -= 8.0 * n;
+                if (n >= 1) per += 32.0;
+            }
             bytes += Nk * per;
         }
     }
@@ -696,7 +752,8 @@ void collect_stats(octane_ctx* c)
     s.kernel_launches = c->launches;
     const Level& F = pl.lv.back();
     s.finest_pixels = (long long)F.g.nx * (F.own1 - F.own0);
-    double f1 = 0, f2 = 0; long long n1 = 0, n2 = 0;
+    double f1 = 0, f2 = 0, fb = 0; long long n1 = 0, n2 = 0;
+    s.pcg_solver = level_fused(c, F) ? 1 : 0;
     // developer switch: one line per timed scope (category, level, solve, iteration, ms)
     FILE* dump = (c->profile && getenv("OCTANE_DUMP_EVENTS")) ? fopen(getenv("OCTANE_DUMP_EVENTS"), "w") : nullptr;
     for (auto& e : c->events) {
@@ -711,16 +768,24 @@ void collect_stats(octane_ctx* c)
             case CAT_TOTAL: s.ms_total += ms; break;
             case CAT_P1:
             case CAT_P2: {
-                const bool worked = e.solve >= 0 && e.ki < c->h_its[e.solve];
+                // ki = -1 is the merged-reduction solver's launch that forms the first alpha: counted in the stage time,
+                // not in the per-iteration average
+                const bool worked = e.solve >= 0 && e.ki >= 0 && e.ki < c->h_its[e.solve];
                 if (e.cat == CAT_P1) { s.ms_pcg_pass1 += ms; if (worked) s.n_pcg_pass1++; }
                 else { s.ms_pcg_pass2 += ms; if (worked) s.n_pcg_pass2++; }
                 if (worked && e.level == s.n_levels - 1) {
-                    if (e.cat == CAT_P1) { f1 += ms; n1++; } else { f2 += ms; n2++; }
+                    if (e.cat == CAT_P1) {
+                        f1 += ms; n1++;
+                        const int q = e.solve - (s.n_levels - 1) * 3 * pl.p.liters;
+                        fb += s.pcg_solver ? fused_bytes(e.ki, q < pl.p.liters)
+                                           : ((e.ki == 0 ? 44.0 : (e.ki == 1 ? 60.0 : 68.0)) - (q < pl.p.liters && pcg_pass1_tma_usable(F.g, F.own1 - F.own0) ? 8.0 : 0.0));
+                    } else { f2 += ms; n2++; }
                 }
             } break;
         }
     }
     if (dump) fclose(dump);
+    s.finest_pass1_bytes_per_px = n1 ? fb / n1 : 0.0;
     s.finest_pass1_ms = n1 ? f1 / n1 : 0.0;
     s.finest_pass2_ms = n2 ? f2 / n2 : 0.0;
 }
@@ -756,7 +821,10 @@ int octane_ctx_create(octane_ctx** out, int device)
     *out = nullptr;
     int n = octane_device_count();
     if (n == 0) { set_err("no CUDA device: octane_b200 has no CPU fallback"); return OCTANE_ENODEV; }
-    if (device < 0 || device >= n) device = 0;    // reference: warning + device 0, :1260-1264
+    if (device < 0 || device >= n) {              // reference: warning + device 0, :1260-1264
+        fprintf(stderr, "octane_b200: device %d is not available (%d visible), using device 0\n", device, n);
+        device = 0;
+    }
     CUDA_OK(cudaSetDevice(device));
     octane_ctx* c = new octane_ctx();
     c->device = device;
@@ -802,6 +870,18 @@ void octane_ctx_destroy(octane_ctx* c)
 
 int octane_ctx_set_profile(octane_ctx* c, int on) { if (!c) return OCTANE_EINVAL; c->profile = on != 0; return OCTANE_OK; }
 int octane_ctx_set_graphs(octane_ctx* c, int on) { if (!c) return OCTANE_EINVAL; c->graphs = on != 0; return OCTANE_OK; }
+
+int octane_ctx_set_solver(octane_ctx* c, int solver)
+{
+    if (!c || (solver != 0 && solver != 1)) { set_err("solver must be 0 (reference recurrence) or 1 (merged reduction)"); return OCTANE_EINVAL; }
+    if (solver != c->solver) {
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        destroy_graphs(c);                                   // the captured PCG loops belong to the other kernels
+        if (c->plan_valid) c->pcg_graph.assign(2 * c->plan.lv.size(), nullptr);
+        c->solver = solver;
+    }
+    return OCTANE_OK;
+}
 
 int octane_ctx_synchronize(octane_ctx* c)
 {
@@ -852,6 +932,12 @@ int band_solve(octane_ctx* c, const float* d_img1, const float* d_img2, const fl
                int nx, int ny, int nc, const octane_params* p, float* d_u, float* d_v)
 {
     begin_call(c);
+    // the two error flags are only ever OR-ed into on the device: clear them per call, so that a context that
+    // reported OCTANE_EHALO / OCTANE_ECOMM once can be used again (e.g. after the caller raised max_disp)
+    if (c->d_scal) {
+        CUDA_OK(cudaSetDevice(c->device));
+        CUDA_OK(cudaMemsetAsync(&c->d_scal->halo_err, 0, 2 * sizeof(int), c->stream));
+    }
     int rc = solve_dev(c, d_img1, d_img2, nx, ny, nc, p, d_fg_u, d_fg_v, d_u, d_v);
     if (rc) return rc;
     if (c->comm.world > 1) {          // halo check needs the device flag
@@ -1623,7 +1709,8 @@ int octane_stage_pcg(octane_ctx* c, const float* d_coef, const float* d_bu, cons
     CUDA_OK(cudaMemsetAsync(B.v, 0, (size_t)g.plane * sizeof(float), st));
     begin_call(c);
     rc = run_pcg(c, L, 0, 0, 0); if (rc) return rc;
-    launch_update_uv(B.u, B.v, B.pcg, g, 0, yi, c->d_its, c->sm_count, st);   // u = 0 + x
+    if (level_fused(c, L)) launch_update_uv_fused(B.u, B.v, B.pcg, g, 0, yi, c->d_its, c->sm_count, st);
+    else launch_update_uv(B.u, B.v, B.pcg, g, 0, yi, c->d_its, c->sm_count, st);   // u = 0 + x
     if ((rc = copy_out(c, d_xu, B.u, g))) return rc;
     if ((rc = copy_out(c, d_xv, B.v, g))) return rc;
     CUDA_OK(cudaMemcpyAsync(c->h_its, c->d_its, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -367,6 +367,41 @@ k_update_uv(float* __restrict__ u, float* __restrict__ v, PcgBuffers b, Geom g, 
     }
 }
 
+// The same after a merged-reduction solve (pcg_fused.cu): x is brought up to date every second iteration (two terms
+// at once), so after an odd number of iterations the last term alpha p is still pending; x exists from the
+// second iteration on and p is single-buffered (pu[0] / pv[0]).
+__global__ void __launch_bounds__(256)
+k_update_uv_fused(float* __restrict__ u, float* __restrict__ v, PcgBuffers b, Geom g, int ja, int jb, int* its_out)
+{
+    const PcgScalars* s = b.scal;
+    const int its = s->its;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && its_out) *its_out = its;
+    if (its == 0) return;
+    const bool pending = (its & 1) != 0, havex = its >= 2;
+    const float alpha = s->alpha;
+    const int upr = g.pitch >> 2;
+    const long long nunits = (long long)(jb - ja) * upr;
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < nunits; t += (long long)gridDim.x * 256) {
+        const int jr = (int)(t / upr), i0 = (int)(t - (long long)jr * upr) * 4;
+        if (i0 >= g.nx) continue;
+        const size_t off = g.at(i0, ja + jr);
+        float4 a = ld4(u + off), c = ld4(v + off);
+        float4 xu = make_float4(0.f, 0.f, 0.f, 0.f), xv = xu, p_u = xu, p_v = xu;
+        if (havex) { xu = ld4(b.xu + off); xv = ld4(b.xv + off); }
+        if (pending) { p_u = ld4(b.pu[0] + off); p_v = ld4(b.pv[0] + off); }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (i0 + k < g.nx) {
+                const float x1 = pending ? fmaf(alpha, el(p_u, k), el(xu, k)) : el(xu, k);     // :1172 of the last iteration
+                const float x2 = pending ? fmaf(alpha, el(p_v, k), el(xv, k)) : el(xv, k);
+                el(a, k) = el(a, k) + x1;                                                        // :1187-1188
+                el(c, k) = el(c, k) + x2;
+            }
+        st4(u + off, a);
+        st4(v + off, c);
+    }
+}
+
 // test hook: the reference's boundary-merged a5..a8 from the stored W, N
 __global__ void __launch_bounds__(256)
 k_expand_coef(PcgBuffers b, Geom g, float* a5, float* a6, float* a7, float* a8)
@@ -438,6 +473,15 @@ void launch_update_uv(float* u, float* v, const PcgBuffers& b, const Geom& g, in
     long long grid = (nunits + 255) / 256;
     if (grid > sm_count * 16) grid = sm_count * 16;
     k_update_uv<<<(int)grid, 256, 0, st>>>(u, v, b, g, ja, jb, its_out);
+}
+
+void launch_update_uv_fused(float* u, float* v, const PcgBuffers& b, const Geom& g, int ja, int jb,
+                            int* its_out, int sm_count, cudaStream_t st)
+{
+    const long long nunits = (long long)(jb - ja) * (g.pitch >> 2);
+    long long grid = (nunits + 255) / 256;
+    if (grid > sm_count * 16) grid = sm_count * 16;
+    k_update_uv_fused<<<(int)grid, 256, 0, st>>>(u, v, b, g, ja, jb, its_out);
 }
 
 void launch_expand_coef(const PcgBuffers& b, const Geom& g, float* a5, float* a6, float* a7, float* a8, cudaStream_t st)

@@ -28,7 +28,8 @@ namespace octane {
 
 namespace {
 
-constexpr int SWMAX = 1024;                 // pixels per strip (256 consumer threads x 4)
+constexpr int SWMAX = 1024;                 // widest strip the stage layout holds
+constexpr int P1PX = 1;                     // pixels per consumer thread (see Consumers below)
 constexpr int HALO = 4;                     // floats of left halo (keeps 16-byte alignment)
 #ifndef OCTANE_P1_NSTAGE
 #define OCTANE_P1_NSTAGE 4        // measured: 4 x 45.3 KB beats 5 (226 of the SM's 227 KB) by 1-3 %
@@ -185,14 +186,15 @@ __device__ __forceinline__ PRowT<PX> p_from_stage(const float* st, int i0s, int 
 }
 
 // The stencil row is latency-bound per warp (dependent FMA chains, shared-memory loads, shuffles),
-// so what keeps the copy engine busy is the number of consumer warps: PX = 2 runs 16 of them
-// (512 threads x 2 pixels), PX = 4 runs 8.  PX = 1 (experimental, OCTANE_P1_PX=1, not measured yet) runs 31:
-// 992 consumer threads + the producer warp fill the 1024-thread block, strips are at most 992 pixels wide.
+// so what keeps the copy engine busy is the number of consumer warps.  Measured on the full disk
+// (profiles/r02_pass1_levers_ab.txt): 8 warps x 4 pixels 5.86 ms per launch, 16 x 2 5.56 ms, 31 x 1 5.06 ms
+// (6.23 TB/s) -- so one pixel per thread ships: 992 consumer threads + the producer warp fill the
+// 1024-thread block, strips are at most 992 pixels wide.
 template <int PX> struct Consumers { static constexpr int N = SWMAX / PX; };
 template <> struct Consumers<1> { static constexpr int N = SWMAX - 32; };
-// CWN (experimental, OCTANE_CONST_WN=1, not measured yet): in the first GNC stage the build stores W = N = -1 at
-// every pixel (al1 = 1: the couplings are -(1 + 0 * psi), build.cu), so the solves of that stage need not read the
-// two planes at all: 8 of pass 1's 68 B/px in a third of the solves.  The boundary multipliers mul_lo / mul_hi
+// CWN: in the first GNC stage the build stores W = N = -1 at every pixel (al1 = 1: the couplings are
+// -(1 + 0 * psi), build.cu), so the solves of that stage do not read the two planes at all: 8 of pass 1's
+// 68 B/px in a third of the solves (measured: full disk 3018 -> 2975 ms per pair, bit-identical results).  The boundary multipliers mul_lo / mul_hi
 // zero the couplings that leave the scene, exactly as they do for the stored planes.
 template <int XM, int PX, bool CWN>
 __global__ void __launch_bounds__(Consumers<PX>::N + 32, 1) k_pcg_pass1_tma(TArgs a)
@@ -429,17 +431,10 @@ void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, in
 {
     TArgs a;
     a.b = b; a.g = g; a.ja = ja; a.jb = jb; a.cur = ki & 1; a.store_halo = store_halo;
-    // developer switches for layout experiments: forced strip width / rows per task
-    static const int force_sw = getenv("OCTANE_P1_SW") ? atoi(getenv("OCTANE_P1_SW")) : 0;
-    static const int force_rs = getenv("OCTANE_P1_RS") ? atoi(getenv("OCTANE_P1_RS")) : 0;
-    // developer switch: pixels per consumer thread (2 -> 16 consumer warps, 4 -> 8, 1 -> 31 with 992-pixel strips)
-    static const int px_env = getenv("OCTANE_P1_PX") ? atoi(getenv("OCTANE_P1_PX")) : 2;
-    static const int px = (px_env == 4 || px_env == 1) ? px_env : 2;
-    const int swmax = (px == 1) ? Consumers<1>::N : SWMAX;
+    constexpr int swmax = Consumers<P1PX>::N;
     a.nstrips = (g.nx + swmax - 1) / swmax;
     a.sw = round_up((g.nx + a.nstrips - 1) / a.nstrips, 32);
     if (a.sw > swmax) a.sw = swmax;
-    if (force_sw >= 32 && force_sw <= swmax) a.sw = round_up(force_sw, 32);
     a.nstrips = (g.nx + a.sw - 1) / a.sw;
     // rows per task: minimise rounds x (rows + 2 halo rows) over the persistent grid
     const int nrows = jb - ja;
@@ -452,22 +447,15 @@ void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, in
         const double cost = (double)rounds * (rs + 2 + 3);      // +3: pipeline fill per task
         if (cost < best_cost) { best_cost = cost; best_rs = rs; }
     }
-    a.rs = force_rs > 0 ? force_rs : best_rs;
+    a.rs = best_rs;
     a.nsegs = (nrows + a.rs - 1) / a.rs;
     const int ntasks = a.nstrips * a.nsegs;
     int grid = ntasks < sm_count ? ntasks : sm_count;
     if (grid > b.max_partial_blocks) grid = b.max_partial_blocks;
     const size_t smem = (size_t)NSTAGE * STAGE_FLOATS * sizeof(float);
     const int xm = ki == 0 ? XM_NONE : (ki == 1 ? XM_INIT : XM_ACC);
-    if (const_wn) {
-        if (px == 2)      launch_variant<2, true>(a, xm, grid, smem, st);
-        else if (px == 1) launch_variant<1, true>(a, xm, grid, smem, st);
-        else              launch_variant<4, true>(a, xm, grid, smem, st);
-    } else {
-        if (px == 2)      launch_variant<2, false>(a, xm, grid, smem, st);
-        else if (px == 1) launch_variant<1, false>(a, xm, grid, smem, st);
-        else              launch_variant<4, false>(a, xm, grid, smem, st);
-    }
+    if (const_wn) launch_variant<P1PX, true>(a, xm, grid, smem, st);
+    else          launch_variant<P1PX, false>(a, xm, grid, smem, st);
 }
 
 }  // namespace octane

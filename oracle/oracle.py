@@ -113,6 +113,8 @@ def lib():
             [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_float, C.c_int, C.c_int, _f32, _f32, _f32]
         L.oracle_apply.argtypes = [_f32, _f32, _f32, C.c_int, C.c_int, _f32, _f32]
         L.oracle_pcg.argtypes = [_f32, _f32, _f32, _f32, _f32, C.c_int, C.c_int, C.c_int, C.c_float, _f32]
+        L.oracle_pcg_merged.argtypes = L.oracle_pcg.argtypes       # model of the product's merged-reduction kernel
+        L.oracle_set_solver.argtypes = [C.c_int]
         L.oracle_pix2uv.argtypes = [C.POINTER(OracleNav), C.c_double, C.c_double, _f32, _f32, C.c_int, C.c_int,
                                     C.c_int, _i16, _i16, _i16, _i16, C.POINTER(C.c_float)]
         L.oracle_pix2uv_ms.argtypes = [C.POINTER(OracleNav), C.c_double, C.c_double, _f32, _f32, C.c_int, C.c_int,

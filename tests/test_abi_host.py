@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/octane_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == names, "python binding list and header disagree"
-    assert L.octane_abi_version() == 2
+    assert L.octane_abi_version() == _lib.EXPECTED_ABI == 3
 
 
 def test_no_torch_types_in_abi():
