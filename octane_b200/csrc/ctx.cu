@@ -194,6 +194,8 @@ struct octane_ctx {
     int* h_its = nullptr;          // pinned
     PcgScalars* h_scal = nullptr;  // pinned
     float* d_gk = nullptr;
+    double* d_navtab = nullptr;    // navigation: constants + per-column / per-row tables of the unmoved pixel
+    size_t navtab_doubles = 0;
     // host-API staging (device)
     char* stage = nullptr;
     size_t stage_bytes = 0;
@@ -691,10 +693,17 @@ int pix2uv_dev_rows(octane_ctx* c, const octane_nav* nav, double t1, double t2, 
     }
     NavParams np;
     fill_nav(np, nav, t1, t2, p);
+    const size_t need = pix2uv_table_doubles(nx, nrows);
+    if (need > c->navtab_doubles) {
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (c->d_navtab) cudaFree(c->d_navtab);
+        c->d_navtab = nullptr; c->navtab_doubles = 0;
+        CUDA_OK(cudaMalloc(&c->d_navtab, need * sizeof(double)));
+        c->navtab_doubles = need;
+    }
     {
         Scope s(c, CAT_NAV);
-        launch_pix2uv(np, d_u, d_v, nx, row0, nrows, U, V, Ur, Vr, c->stream);
-        c->launches++;
+        c->launches += launch_pix2uv(np, d_u, d_v, nx, row0, nrows, c->d_navtab, U, V, Ur, Vr, c->stream);
     }
     CUDA_OK(cudaGetLastError());
     return OCTANE_OK;
@@ -860,6 +869,7 @@ void octane_ctx_destroy(octane_ctx* c)
     if (c->d_partials) cudaFree(c->d_partials);
     if (c->d_its) cudaFree(c->d_its);
     if (c->d_gk) cudaFree(c->d_gk);
+    if (c->d_navtab) cudaFree(c->d_navtab);
     if (c->h_its) cudaFreeHost(c->h_its);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }

@@ -112,8 +112,11 @@ struct NavParams {
     double t1, t2;
     int pixuv, dp, dm;
 };
-void launch_pix2uv(const NavParams& np, const float* u, const float* v, int nx, int row0, int nrows,
-                   short* U, short* V, short* Uraw, short* Vraw, cudaStream_t st);
+// tab: device scratch of pix2uv_table_doubles(nx, nrows) doubles (constants + per-column / per-row tables of the
+// unmoved pixel, filled by a setup kernel on the same stream); returns the number of launches
+size_t pix2uv_table_doubles(int nx, int nrows);
+int launch_pix2uv(const NavParams& np, const float* u, const float* v, int nx, int row0, int nrows, double* tab,
+                  short* U, short* V, short* Uraw, short* Vraw, cudaStream_t st);
 void launch_ctp_pack(const float* cth, short* ctp, size_t n, int ir, cudaStream_t st);
 
 
