@@ -339,14 +339,17 @@ class Context:
     def stage_blur_decimate(self, d_img, nx, ny, nc, factor, d_out):
         self._after_torch()
         self._check(self._L.octane_stage_blur_decimate(self._h, _ptr(d_img), nx, ny, nc, factor, _ptr(d_out)))
+        self._before_torch()
 
     def stage_gradient(self, d_f, xi, yi, nc, d_gx, d_gy):
         self._after_torch()
         self._check(self._L.octane_stage_gradient(self._h, _ptr(d_f), xi, yi, nc, _ptr(d_gx), _ptr(d_gy)))
+        self._before_torch()
 
     def stage_zoom_in(self, d_flow, nx, ny, nxx, nyy, sf, d_out):
         self._after_torch()
         self._check(self._L.octane_stage_zoom_in(self._h, _ptr(d_flow), nx, ny, nxx, nyy, sf, _ptr(d_out)))
+        self._before_torch()
 
     # ---- ingest (src/oct_navcal_cuda.cu:100) and first-guess conversion (src/oct_pix2uv_cuda.cu:372)
     def oct_navcal_cuda(self, rad, x, y, nav: Nav, cal: Cal, data=None, lat=None, lon=None):
@@ -359,14 +362,21 @@ class Context:
             data = mk() if data is None else data
             lat = mk() if lat is None else lat
             lon = mk() if lon is None else lon
+            for name, arr in (("rad", rad), ("x", x), ("y", y)):
+                _require(name, arr, "int16", cuda=True)
+            for name, arr in (("data", data), ("lat", lat), ("lon", lon)):
+                _require(name, arr, "float32", cuda=True)
             self._after_torch()
             self._check(self._L.octane_navcal_dev(self._h, _ptr(rad), _ptr(x), _ptr(y), nx, ny, C.byref(nav),
                                                   C.byref(cal), _ptr(data), _ptr(lat), _ptr(lon)))
+            self._before_torch()       # the outputs were allocated on torch's stream: order it after our kernel
             return data, lat, lon
         rad = np.ascontiguousarray(rad, np.int16); x = np.ascontiguousarray(x, np.int16); y = np.ascontiguousarray(y, np.int16)
         data = np.empty((ny, nx), np.float32) if data is None else data
         lat = np.empty((ny, nx), np.float32) if lat is None else lat
         lon = np.empty((ny, nx), np.float32) if lon is None else lon
+        for name, arr in (("data", data), ("lat", lat), ("lon", lon)):
+            _require(name, arr, "float32", cuda=False)
         self._check(self._L.octane_navcal(self._h, _ptr(rad), _ptr(x), _ptr(y), nx, ny, C.byref(nav), C.byref(cal),
                                           _ptr(data), _ptr(lat), _ptr(lon)))
         return data, lat, lon
@@ -386,9 +396,11 @@ class Context:
         ny, nx = field.shape
         if _is_torch(field):
             import torch
+            _require("field", field, "float32", cuda=True)
             out = torch.empty((nyy, nxx), dtype=torch.float32, device=field.device)
             self._after_torch()
             self._check(self._L.octane_zoom_in_float_dev(self._h, _ptr(field), nx, ny, _ptr(out), nxx, nyy, interp))
+            self._before_torch()
             return out
         field = np.ascontiguousarray(field, np.float32)
         out = np.empty((nyy, nxx), np.float32)
@@ -402,9 +414,11 @@ class Context:
         nxx, nyy = zoom_out_size(nx, ny, factor)
         if _is_torch(field):
             import torch
+            _require("field", field, "float32", cuda=True)
             out = torch.empty((nyy, nxx), dtype=torch.float32, device=field.device)
             self._after_torch()
             self._check(self._L.octane_zoom_out_float_dev(self._h, _ptr(field), nx, ny, _ptr(out), factor))
+            self._before_torch()
             return out
         field = np.ascontiguousarray(field, np.float32)
         out = np.empty((nyy, nxx), np.float32)
@@ -421,6 +435,7 @@ class Context:
             _require("cth", cth, "float32", cuda=True)
             self._after_torch()
             self._check(self._L.octane_srsal_dev(self._h, _ptr(upix), _ptr(vpix), _ptr(cth), nx, ny))
+            self._before_torch()
             return upix, vpix
         cth = np.ascontiguousarray(cth, np.float32)
         self._check(self._L.octane_srsal(self._h, _ptr(upix), _ptr(vpix), _ptr(cth), nx, ny))
@@ -431,10 +446,17 @@ class Context:
         sector-moved guard zeroed them."""
         p = p or default_params()
         ny, nx = u.shape
-        if _is_torch(u):
+        dev = _is_torch(u)
+        for name, arr in (("lat", lat), ("lon", lon), ("u", u), ("v", v)):
+            _require(name, arr, "float32", cuda=dev)
+        for name, arr in (("x", x), ("y", y)):
+            _require(name, arr, "int16", cuda=dev)
+        if dev:
             self._after_torch()
-            return self._check(self._L.octane_uv2pix_dev(self._h, C.byref(nav), t1, t2, _ptr(lat), _ptr(lon), _ptr(x),
-                                                         _ptr(y), nx, ny, C.byref(p), _ptr(u), _ptr(v)))
+            rc = self._check(self._L.octane_uv2pix_dev(self._h, C.byref(nav), t1, t2, _ptr(lat), _ptr(lon), _ptr(x),
+                                                       _ptr(y), nx, ny, C.byref(p), _ptr(u), _ptr(v)))
+            self._before_torch()
+            return rc
         return self._check(self._L.octane_uv2pix(self._h, C.byref(nav), t1, t2, _ptr(lat), _ptr(lon), _ptr(x), _ptr(y),
                                                  nx, ny, C.byref(p), _ptr(u), _ptr(v)))
 
@@ -443,10 +465,12 @@ class Context:
         self._check(self._L.octane_stage_build(self._h, _ptr(d_u), _ptr(d_v), _ptr(d_uh), _ptr(d_vh), _ptr(d_g1),
                                                _ptr(d_g2), xi, yi, nc, C.byref(p), lambdac, gnc, _ptr(d_coef),
                                                _ptr(d_bu), _ptr(d_bv)))
+        self._before_torch()
 
     def stage_pcg(self, d_coef, d_bu, d_bv, xi, yi, iters, tol, d_xu, d_xv) -> int:
         its = C.c_int()
         self._after_torch()
         self._check(self._L.octane_stage_pcg(self._h, _ptr(d_coef), _ptr(d_bu), _ptr(d_bv), xi, yi, iters, tol,
                                              _ptr(d_xu), _ptr(d_xv), C.byref(its)))
+        self._before_torch()
         return its.value

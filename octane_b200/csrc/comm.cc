@@ -26,7 +26,7 @@ struct Api {
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 Api api;
-char errbuf[512] = "";
+thread_local char errbuf[512] = "";      // per thread, like ctx.cu's g_err: two contexts on two host threads do not share it
 
 bool load()
 {
