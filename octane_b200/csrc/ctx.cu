@@ -176,6 +176,7 @@ struct octane_ctx {
     // (pcg_fused.cu, the default); 0 = the reference's recurrence literally, two launches (pcg_tma.cu + pcg.cu).
     // Small levels always run the latter (octane_ctx_set_solver).
     int solver = 1;
+    bool coop = true;        // small levels: one cooperative launch per solve (falls back to per-iteration launches)
     Comm comm;
     // workspace
     char* arena = nullptr;
@@ -457,10 +458,26 @@ int enqueue_pcg(octane_ctx* c, const Level& L, int level, int solve, int const_w
     return OCTANE_OK;
 }
 
-// const_wn: the system was built in the first GNC stage (W = N = -1 everywhere) and the context opted in
+// small levels on one GPU: the whole solve in one cooperative launch (pcg.cu: k_pcg_coop)
+bool level_coop(const octane_ctx* c, const Level& L)
+{
+    // "small" = below the size the TMA-fed kernels take (either solver)
+    return c->coop && c->comm.world <= 1 && !pcg_fused_usable(L.g, L.own1 - L.own0);
+}
+
+// const_wn: the system was built in the first GNC stage (W = N = -1 everywhere)
 int run_pcg(octane_ctx* c, const Level& L, int level, int solve, int const_wn)
 {
     if (c->plan.p.cgiters <= 0) return OCTANE_OK;
+    if (level_coop(c, L)) {
+        Scope s(c, CAT_P1, level, solve, -2);           // ki = -2: a whole solve, not an iteration
+        if (launch_pcg_coop(c->buf.pcg, L.g, L.own0, L.own1, c->plan.p.cgiters, c->sm_count, c->stream) == 0) {
+            c->launches++;
+            return OCTANE_OK;
+        }
+        cudaGetLastError();                              // e.g. a device that cannot co-schedule the grid: per-iteration launches
+        c->coop = false;
+    }
     if (!c->graphs || c->profile) return enqueue_pcg(c, L, level, solve, const_wn);
     const size_t slot = 2 * (size_t)level + (const_wn ? 1 : 0);
     if (!c->pcg_graph[slot]) {

@@ -82,6 +82,9 @@ bool pcg_pass1_tma_usable(const Geom& g, int nrows);
 void launch_pcg_pass1_tma(const PcgBuffers& b, const Geom& g, int ja, int jb, int ki, int store_halo,
                           int sm_count, cudaStream_t st, int const_wn = 0);
 void launch_pcg_pass2(const PcgBuffers& b, const Geom& g, int ja, int jb, int sm_count, cudaStream_t st);
+// small levels on one GPU: the whole solve (up to `iters` iterations of the same two passes, same recurrence) in one
+// cooperative launch with grid-wide barriers instead of 2 x iters launches; returns 0, or -1 when the launch fails
+int launch_pcg_coop(const PcgBuffers& b, const Geom& g, int ja, int jb, int iters, int sm_count, cudaStream_t st);
 // u += x + alpha_last p_last, v likewise (:1185-1195 with the pending x term folded in)
 void launch_update_uv(float* u, float* v, const PcgBuffers& b, const Geom& g, int ja, int jb,
                       int* its_out, int sm_count, cudaStream_t st);

@@ -19,6 +19,8 @@
 // Every launch re-reads the device-side `done` flag and returns at once when
 // the stop rule has fired, so the host can enqueue the cap's worth of launches
 // (or replay a CUDA graph of them) without synchronising.
+#include <cooperative_groups.h>
+
 #include "kernels.cuh"
 
 namespace octane {
@@ -57,7 +59,7 @@ struct PRow {
 // (1/M) as jDiagInv (:142-149): 1./M rounded to float; z = Minv*r (:1117,1138);
 // p = Bk*p + z (:1146, one FMA).
 template <int XM>
-__device__ __forceinline__ PRow compute_p(const P1Args& a, int j, int i0, int lane, float beta, float alpha_prev,
+__device__ __forceinline__ PRow compute_p(const P1Args& a, int cur, int j, int i0, int lane, float beta, float alpha_prev,
                                           bool own)
 {
     constexpr bool FIRST = (XM == XM_NONE);
@@ -66,8 +68,8 @@ __device__ __forceinline__ PRow compute_p(const P1Args& a, int j, int i0, int la
     o.eu = o.ev = 0.f;
     const Geom& g = a.g;
     if (j < 0 || j >= g.ny) return o;
-    const float* pu_old = a.b.pu[a.cur];
-    const float* pv_old = a.b.pv[a.cur];
+    const float* pu_old = a.b.pu[cur];
+    const float* pv_old = a.b.pv[cur];
     if (i0 < g.nx) {
         const size_t off = g.at(i0, j);
         const float4 ru = ld4(a.b.ru + off), rv = ld4(a.b.rv + off);
@@ -118,20 +120,17 @@ __device__ __forceinline__ PRow compute_p(const P1Args& a, int j, int i0, int la
 __device__ __forceinline__ float mul_lo(int i, int n) { return i == 0 ? 0.f : (i == n - 1 ? 2.f : 1.f); }
 __device__ __forceinline__ float mul_hi(int i, int n) { return i == n - 1 ? 0.f : (i == 0 ? 2.f : 1.f); }
 
+// q = A p of this block's share of the (strip x row segment) tasks, p and x updated on the way; returns the
+// thread's partial p.q.  Shared by the per-iteration kernel and the whole-solve cooperative kernel.
 template <int XM>
-__global__ void __launch_bounds__(256, 2) k_pcg_pass1(P1Args a)
+__device__ __forceinline__ double pass1_tasks(const P1Args& a, int cur, float beta, float alpha_prev)
 {
     constexpr bool FIRST = (XM == XM_NONE);
-    __shared__ double red[32];
-    const PcgScalars* s = a.b.scal;
-    if (s->done) return;
-    const float beta = FIRST ? 0.f : s->rz / s->rz_old;      // Bk, :1144
-    const float alpha_prev = FIRST ? 0.f : s->alpha;
     const Geom& g = a.g;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int ntasks = a.nstrips * a.nsegs;
-    float* pu_new = a.b.pu[a.cur ^ 1];
-    float* pv_new = a.b.pv[a.cur ^ 1];
+    float* pu_new = a.b.pu[cur ^ 1];
+    float* pv_new = a.b.pv[cur ^ 1];
     const float* W = a.b.coef[C_W];
     const float* N = a.b.coef[C_N];
     double dot[1] = { 0.0 };
@@ -141,8 +140,8 @@ __global__ void __launch_bounds__(256, 2) k_pcg_pass1(P1Args a)
         const int i0 = strip * 128 + lane * 4;
         const int j_a = a.ja + seg * a.rs, j_b = min(a.jb, j_a + a.rs);
         const bool active = i0 < g.nx;
-        PRow up = compute_p<XM>(a, j_a - 1, i0, lane, beta, alpha_prev, false);
-        PRow ce = compute_p<XM>(a, j_a, i0, lane, beta, alpha_prev, true);
+        PRow up = compute_p<XM>(a, cur, j_a - 1, i0, lane, beta, alpha_prev, false);
+        PRow ce = compute_p<XM>(a, cur, j_a, i0, lane, beta, alpha_prev, true);
         float4 n_up = make_float4(0.f, 0.f, 0.f, 0.f);                 // N of the row above the centre
         if (active && j_a > 0) n_up = ld4(N + g.at(i0, j_a - 1));
         if (a.store_halo && j_a == a.ja && j_a - 1 >= 0 && active) {
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(256, 2) k_pcg_pass1(P1Args a)
             st4(pv_new + g.at(i0, j_a - 1), up.pv);
         }
         for (int j = j_a; j < j_b; j++) {
-            PRow dn = compute_p<XM>(a, j + 1, i0, lane, beta, alpha_prev, j + 1 < j_b);
+            PRow dn = compute_p<XM>(a, cur, j + 1, i0, lane, beta, alpha_prev, j + 1 < j_b);
             // horizontal neighbours of the centre row: lanes exchange their edge pixels
             float lu = __shfl_up_sync(0xffffffffu, ce.pu.w, 1), lv = __shfl_up_sync(0xffffffffu, ce.pv.w, 1);
             float ru_ = __shfl_down_sync(0xffffffffu, ce.pu.x, 1), rv_ = __shfl_down_sync(0xffffffffu, ce.pv.x, 1);
@@ -213,6 +212,19 @@ __global__ void __launch_bounds__(256, 2) k_pcg_pass1(P1Args a)
             st4(pv_new + g.at(i0, j_b), ce.pv);
         }
     }
+    return dot[0];
+}
+
+template <int XM>
+__global__ void __launch_bounds__(256, 2) k_pcg_pass1(P1Args a)
+{
+    constexpr bool FIRST = (XM == XM_NONE);
+    __shared__ double red[32];
+    const PcgScalars* s = a.b.scal;
+    if (s->done) return;
+    const float beta = FIRST ? 0.f : s->rz / s->rz_old;      // Bk, :1144
+    const float alpha_prev = FIRST ? 0.f : s->alpha;
+    double dot[1] = { pass1_tasks<XM>(a, a.cur, beta, alpha_prev) };
     block_sum<1>(dot, red);
     double tot[1];
     if (grid_sum_finish<1>(dot, a.b.partials, a.b.ticket, tot, red)) {
@@ -224,25 +236,16 @@ __global__ void __launch_bounds__(256, 2) k_pcg_pass1(P1Args a)
     }
 }
 
-struct P2Args {
-    PcgBuffers b;
-    Geom g;
-    int ja, jb;
-};
+typedef P1Args P2Args;       // pass 2 reads b, g, ja, jb of the same argument block
 
-// r -= alpha q; partial r.r and z.r; the last block rolls the scalars and applies the stop rule.
-__global__ void __launch_bounds__(256) k_pcg_pass2(P2Args a)
+// r -= alpha q over this block's share of the rows; acc += partial r.r and z.r.  Shared by the per-iteration kernel
+// and the whole-solve cooperative kernel.
+__device__ __forceinline__ void pass2_units(const P1Args& a, float alphak, bool p2p, double (&acc)[2])
 {
-    __shared__ double red[2 * 32];
-    PcgScalars* s = a.b.scal;
-    if (s->done) return;
-    const float alphak = s->rz / s->pAp;                      // :1169
     const float nalpha = -1. * alphak;                        // :1174
     const Geom& g = a.g;
-    const bool p2p = a.b.p2p.world > 1;
     const int upr = g.pitch >> 2;                             // float4 units per row
     const long long nunits = (long long)(a.jb - a.ja) * upr;
-    double acc[2] = { 0.0, 0.0 };
     for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < nunits; t += (long long)gridDim.x * 256) {
         const int jr = (int)(t / upr), i0 = (int)(t - (long long)jr * upr) * 4;
         if (i0 >= g.nx) continue;
@@ -277,6 +280,18 @@ __global__ void __launch_bounds__(256) k_pcg_pass2(P2Args a)
         acc[0] += (double)prr;
         acc[1] += (double)prz;
     }
+}
+
+// r -= alpha q; partial r.r and z.r; the last block rolls the scalars and applies the stop rule.
+__global__ void __launch_bounds__(256) k_pcg_pass2(P2Args a)
+{
+    __shared__ double red[2 * 32];
+    PcgScalars* s = a.b.scal;
+    if (s->done) return;
+    const float alphak = s->rz / s->pAp;                      // :1169
+    const bool p2p = a.b.p2p.world > 1;
+    double acc[2] = { 0.0, 0.0 };
+    pass2_units(a, alphak, p2p, acc);
     block_sum<2>(acc, red);
     double tot[2];
     if (grid_sum_finish<2>(acc, a.b.partials, a.b.ticket, tot, red, p2p)) {
@@ -293,6 +308,79 @@ __global__ void __launch_bounds__(256) k_pcg_pass2(P2Args a)
             s->its = s->its + 1;
             s->done = !(rr > s->tol);          // while((*residc) > tol ...), :1131
         }
+    }
+}
+
+// ---- a whole solve in ONE cooperative launch (small levels, one GPU) ------------------------------------------
+// A 500 x 500 level is a few microseconds of work per pass: 60 launches per solve spend their time in launch
+// latency and in the GPU's front end (64 pairs in flight on 8 to 32 streams all run at the same 1.6 us per kernel,
+// profiles/r02_bench_batch64_streams*.json).  Here the same two passes of the same recurrence run inside one kernel,
+// separated by grid-wide barriers; every block sums the per-block partials itself, in the same fixed order, so all
+// blocks take the same alpha, beta and stop decision without a ticket or a scalar round trip through memory.
+template <int NV>
+__device__ __forceinline__ void coop_sum(double (&v)[NV], double* partials, double* red, cooperative_groups::grid_group& grid)
+{
+    const int tid = threadIdx.x;
+    block_sum<NV>(v, red);
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) partials[(size_t)k * gridDim.x + blockIdx.x] = v[k];
+    }
+    grid.sync();
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double t = 0.0;
+        for (unsigned b = tid; b < gridDim.x; b += 256) t += __ldcg(&partials[(size_t)k * gridDim.x + b]);
+        v[k] = t;
+    }
+    __syncthreads();                       // red is reused
+    block_sum<NV>(v, red);
+    // broadcast thread 0's totals to the block
+    __shared__ double bc[NV];
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) bc[k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = bc[k];
+}
+
+__global__ void __launch_bounds__(256, 2) k_pcg_coop(P1Args a, int iters)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[2 * 32];
+    PcgScalars* s = a.b.scal;
+    // the scalars of the solve live in registers, identically in every thread of the grid
+    float rz = s->rz, rr = s->rr, rz_old = 0.f, alpha = 0.f;
+    const float tol = s->tol;
+    int its = 0;
+    bool done = s->done != 0;
+    double* part1 = a.b.partials;                       // p.q
+    double* part2 = a.b.partials + gridDim.x;           // r.r, z.r (two more regions: a block may still read one while
+                                                        // a faster block already writes the other)
+    for (int ki = 0; ki < iters && !done; ki++) {
+        const int cur = ki & 1;
+        double d1[1];
+        if (ki == 0)      d1[0] = pass1_tasks<XM_NONE>(a, cur, 0.f, 0.f);
+        else if (ki == 1) d1[0] = pass1_tasks<XM_INIT>(a, cur, rz / rz_old, alpha);       // Bk, :1144
+        else              d1[0] = pass1_tasks<XM_ACC>(a, cur, rz / rz_old, alpha);
+        coop_sum<1>(d1, part1, red, grid);
+        const float pAp = (float)d1[0];                                              // pkTApk, :1165
+        const float alphak = rz / pAp;                                               // :1169
+        double d2[2] = { 0.0, 0.0 };
+        pass2_units(a, alphak, false, d2);
+        coop_sum<2>(d2, part2, red, grid);
+        alpha = alphak;
+        rz_old = rz;
+        rz = (float)d2[1];
+        rr = (float)d2[0];
+        its++;
+        done = !(rr > tol);                                                          // :1131
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        s->alpha = alpha; s->rz_old = rz_old; s->rz = rz; s->rr = rr; s->its = its; s->done = done ? 1 : 0;
     }
 }
 
@@ -454,10 +542,33 @@ void launch_pcg_pass1(const PcgBuffers& b, const Geom& g, int ja, int jb, int ki
     else              k_pcg_pass1<XM_ACC><<<grid, 256, 0, st>>>(a);
 }
 
+// grid of the cooperative whole-solve kernel: enough blocks for the level's warp tasks, never more than fit on the
+// device at once (2 blocks of 256 threads per SM by the launch bounds; the occupancy query has the last word)
+int launch_pcg_coop(const PcgBuffers& b, const Geom& g, int ja, int jb, int iters, int sm_count, cudaStream_t st)
+{
+    P1Args a;
+    a.b = b; a.g = g; a.ja = ja; a.jb = jb; a.cur = 0; a.store_halo = 0;
+    a.nstrips = (g.nx + 127) / 128;
+    a.rs = pass1_rows_per_task(a.nstrips, jb - ja, sm_count);
+    a.nsegs = (jb - ja + a.rs - 1) / a.rs;
+    static int per_sm = 0;
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_coop, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    const int ntasks = a.nstrips * a.nsegs;
+    int grid = (ntasks + 7) / 8;
+    const int cap = sm_count * per_sm;
+    if (grid > cap) grid = cap;
+    if (3 * grid > 2 * b.max_partial_blocks) grid = 2 * b.max_partial_blocks / 3;
+    if (grid < 1) grid = 1;
+    void* args[] = { &a, &iters };
+    return cudaLaunchCooperativeKernel((const void*)k_pcg_coop, dim3(grid), dim3(256), args, 0, st) == cudaSuccess ? 0 : -1;
+}
+
 void launch_pcg_pass2(const PcgBuffers& b, const Geom& g, int ja, int jb, int sm_count, cudaStream_t st)
 {
     P2Args a;
-    a.b = b; a.g = g; a.ja = ja; a.jb = jb;
+    a.b = b; a.g = g; a.ja = ja; a.jb = jb; a.cur = 0; a.store_halo = 0; a.rs = 0; a.nstrips = 0; a.nsegs = 0;
     const long long nunits = (long long)(jb - ja) * (g.pitch >> 2);
     long long grid = (nunits + 255) / 256;
     const int cap = sm_count * 16;
