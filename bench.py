@@ -610,48 +610,74 @@ def main():
     # A function of its own: the pinned buffers must be released while the context's stream is still
     # alive (torch's host allocator records an event on every stream a pinned block was used on).
     def run_e2e():
-        if world == 1:
-            h1 = torch.empty((ny, nx), dtype=torch.float32, pin_memory=True); h1.copy_(img1)
-            h2 = torch.empty((ny, nx), dtype=torch.float32, pin_memory=True); h2.copy_(img2)
-            hu = torch.zeros((ny, nx), dtype=torch.float32, pin_memory=True)
-            hv = torch.zeros((ny, nx), dtype=torch.float32, pin_memory=True)
-            n1, n2 = h1.numpy(), h2.numpy()
-            hs = {k: torch.zeros((ny, nx), dtype=torch.int16, pin_memory=True).numpy()
-                  for k in ("uVal", "vVal", "uVal2", "vVal2")}
+        """End to end through the C ABI with pinned HOST buffers: every pair's band goes host -> device, its pixel
+        displacements (float) and the four short planes come back, all inside the timed region.
+        N = 1, `latency`: octane_optical_flow, one blocking call per pair (copy-in, solve, navigation, copy-out in sequence,
+        the copy-out of the displacements overlapping the navigation).
+        `value`: the pipelined dispatcher octane_stream_submit / octane_stream_wait over the sequence of pairs of the
+        timed region -- two pairs in flight, so the copies of pair k+1 and k-1 run under the solve of pair k.  It is the
+        loop an archive reprocessing run makes; per-pair latency is reported beside it."""
+        nin = in1 - in0
+        h1 = torch.empty((nin, nx), dtype=torch.float32, pin_memory=True); h1.copy_(img1)
+        h2 = torch.empty((nin, nx), dtype=torch.float32, pin_memory=True); h2.copy_(img2)
+        n1, n2 = h1.numpy(), h2.numpy()
+        outs = [{k: torch.zeros((nown, nx), dtype=(torch.float32 if k.endswith("Pix") else torch.int16), pin_memory=True).numpy()
+                 for k in ("uPix", "vPix", "uVal", "vVal", "uVal2", "vVal2")} for _ in range(2)]
+        state = {"k": 0}
 
-            def e2e_step():
-                ctx.oct_optical_flow(n1, n2, nav, 0.0, dt, p, upix=hu.numpy(), vpix=hv.numpy(), out=hs)
+        def submit_next():
+            k = state["k"]
+            ctx.stream_submit(k % 2, n1, n2, nav, 0.0, dt, p, outs[k % 2], nx, ny)
+            if k > 0:
+                ctx.stream_wait((k - 1) % 2)
+            state["k"] = k + 1
 
-            h2d = 2 * nx * ny * 4
-            d2h = nx * ny * (2 * 4 + 4 * 2)
-        else:
-            h1 = torch.empty(img1.shape, dtype=torch.float32, pin_memory=True); h1.copy_(img1)
-            h2 = torch.empty(img2.shape, dtype=torch.float32, pin_memory=True); h2.copy_(img2)
-            hu = torch.zeros((nown, nx), dtype=torch.float32, pin_memory=True)
-            hv = torch.zeros_like(hu).pin_memory()
-            hs = [torch.zeros((nown, nx), dtype=torch.int16, pin_memory=True) for _ in range(4)]
+        def drain():
+            if state["k"] > 0:
+                ctx.stream_wait((state["k"] - 1) % 2)
 
-            def e2e_step():
-                with torch.cuda.stream(stream):
-                    img1.copy_(h1, non_blocking=True); img2.copy_(h2, non_blocking=True)
-                    ctx.oct_variational_optical_flow_band(img1, img2, u, v, nx, ny, p)
-                    ctx.oct_pix2uv_band(nav, 0.0, dt, u, v, nx, own0, nown, *shorts, p)
-                    hu.copy_(u, non_blocking=True); hv.copy_(v, non_blocking=True)
-                    for a, b in zip(hs, shorts):
-                        a.copy_(b, non_blocking=True)
-                ctx.synchronize()
+        def pipelined(steps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                submit_next()
+            drain()                               # the last pair's outputs are in host memory
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if dist:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms / steps
 
-            h2d = 2 * nx * (in1 - in0) * 4
-            d2h = nx * nown * (2 * 4 + 4 * 2)
-        for _ in range(min(args.warmup, 1)):
-            e2e_step()
-        ms_e2e = timed(e2e_step, args.steps)
+        for _ in range(max(2, min(args.warmup, 3))):
+            submit_next()
+        drain()
+        ms_e2e = pipelined(args.steps)
+        # per-pair latency: one pair at a time through the same entry points
+        def one():
+            ctx.stream_submit(0, n1, n2, nav, 0.0, dt, p, outs[0], nx, ny)
+            ctx.stream_wait(0)
+        ms_lat = timed(one, min(args.steps, 3))
         res = {"value": mpix / (ms_e2e / 1e3), "unit": "Mpix/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "api": "octane_optical_flow (host buffers, pinned)" if world == 1 else
-                      "pinned band H2D + octane_variational_flow_band_dev + octane_pix2uv_band_dev + D2H"}
-        return res
+               "h2d_bytes_per_step": 2 * nx * nin * 4, "d2h_bytes_per_step": nx * nown * (2 * 4 + 4 * 2),
+               "api": "octane_stream_submit / octane_stream_wait (pinned host buffers; two pairs in flight: the copies of one "
+                      "pair run under the solve of the other; every pair's H2D and D2H are inside the timed region)",
+               "latency_ms_per_pair": ms_lat, "latency_Mpix/s": mpix / (ms_lat / 1e3),
+               "latency_api": "one pair at a time: submit + wait (copy-in, solve, navigation, copy-out in sequence)"}
+        if world == 1:
+            hs = {k: outs[1][k] for k in ("uVal", "vVal", "uVal2", "vVal2")}
 
+            def blocking():
+                ctx.oct_optical_flow(n1, n2, nav, 0.0, dt, p, upix=outs[1]["uPix"], vpix=outs[1]["vPix"], out=hs)
+
+            blocking()
+            ms_blk = timed(blocking, min(args.steps, 3))
+            res["blocking_call"] = {"api": "octane_optical_flow (host buffers, pinned)", "ms_per_step": ms_blk,
+                                    "Mpix/s": mpix / (ms_blk / 1e3)}
+        return res
 
     # the flow of the last timed step, checked against the stored single-GPU digest (every rank contributes its rows)
     check = flow_check(u, v, own0, nx, ny, args.workload, dist, args.write_digest and world == 1)

@@ -297,6 +297,21 @@ int octane_pix2uv_band_dev(octane_ctx* ctx, const octane_nav* nav, double t1, do
                            const octane_params* p,
                            short* d_U, short* d_V, short* d_U_raw, short* d_V_raw);
 
+/* ---- pipelined host-buffer dispatcher (sequences of pairs; one GPU or row bands) -------
+ * The reference processes one pair per run (src/main.cc:439 -> oct_optical_flow, src/oct_optical_flow.cc:21);
+ * an archive or a 1-minute mesoscale sequence is a loop over pairs.  octane_stream_submit enqueues, for one pair,
+ * copy-in -> solve -> CTP pack -> navigation -> copy-out on three streams and returns; octane_stream_wait blocks
+ * until that pair's outputs are in host memory.  Two pairs may be in flight (slot 0 / 1), so the copies of one
+ * pair run under the solve of the other.  Host buffers must be pinned for the overlap to happen and stay valid
+ * until the wait returns.  img*: rows [in0,in1) of octane_band_plan (the whole scene on one GPU); every output:
+ * rows [own0,own1).  upix/vpix may both be NULL (the reference writes them only with -pd).  No first guess, no
+ * -srsal here.  In banded runs every rank submits the same sequence.  Returns 1 when the sector-moved guard
+ * zeroed the navigated outputs. */
+int octane_stream_submit(octane_ctx* ctx, int slot, const float* img1_band, const float* img2_band, const float* cth_own,
+                         int nx, int ny, int nc, const octane_nav* nav, double t1, double t2, const octane_params* p,
+                         float* upix_own, float* vpix_own, short* U, short* V, short* U_raw, short* V_raw, short* ctp_own);
+int octane_stream_wait(octane_ctx* ctx, int slot);
+
 #ifdef __cplusplus
 }
 #endif

@@ -335,6 +335,27 @@ class Context:
             self._before_torch()
         return rc
 
+    # ---- pipelined dispatcher over a sequence of pairs (host buffers, ideally pinned)
+    def stream_submit(self, slot: int, geo1_band, geo2_band, nav: Nav, t1: float, t2: float, p: Params, out: dict,
+                      nx: int, ny: int, cth=None, nc: int = 1) -> int:
+        """enqueue copy-in -> solve -> navigation -> copy-out of one pair and return.  geo*_band: rows [in0,in1) of
+        band_plan() (the whole scene on one GPU); `out`: host arrays for rows [own0,own1) under the keys uVal, vVal,
+        uVal2, vVal2 (int16) and optionally uPix, vPix (float32), CTP (int16).  The arrays must stay alive and untouched
+        until stream_wait(slot)."""
+        for name, a in (("geo1_band", geo1_band), ("geo2_band", geo2_band), ("cth", cth), ("uPix", out.get("uPix")),
+                        ("vPix", out.get("vPix"))):
+            _require(name, a, "float32", cuda=False)
+        for name in ("uVal", "vVal", "uVal2", "vVal2"):
+            _require(name, out[name], "int16", cuda=False)
+        _require("CTP", out.get("CTP"), "int16", cuda=False)
+        return self._check(self._L.octane_stream_submit(self._h, slot, _ptr(geo1_band), _ptr(geo2_band), _ptr(cth), nx, ny, nc,
+                                                        C.byref(nav), t1, t2, C.byref(p), _ptr(out.get("uPix")),
+                                                        _ptr(out.get("vPix")), _ptr(out["uVal"]), _ptr(out["vVal"]),
+                                                        _ptr(out["uVal2"]), _ptr(out["vVal2"]), _ptr(out.get("CTP"))))
+
+    def stream_wait(self, slot: int):
+        self._check(self._L.octane_stream_wait(self._h, slot))
+
     # ---- stage entry points (device pointers; parity tests)
     def stage_blur_decimate(self, d_img, nx, ny, nc, factor, d_out):
         self._after_torch()

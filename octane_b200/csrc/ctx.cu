@@ -197,6 +197,15 @@ struct octane_ctx {
     float* d_gk = nullptr;
     double* d_navtab = nullptr;    // navigation: constants + per-column / per-row tables of the unmoved pixel
     size_t navtab_doubles = 0;
+    // pipelined host-buffer dispatcher (octane_stream_submit / _wait): two slots of device staging, so that the
+    // copies of one pair overlap the solve of the other
+    struct StreamSlot {
+        char* buf = nullptr;
+        size_t bytes = 0;
+        cudaEvent_t in_ready = nullptr, in_free = nullptr, out_ready = nullptr, done = nullptr;
+        bool busy = false;
+    } slot[2];
+    cudaStream_t h2d_stream = nullptr;
     // host-API staging (device)
     char* stage = nullptr;
     size_t stage_bytes = 0;
@@ -714,6 +723,12 @@ int pix2uv_dev_rows(octane_ctx* c, const octane_nav* nav, double t1, double t2, 
     if (need > c->navtab_doubles) {
         CUDA_OK(cudaStreamSynchronize(c->stream));
         if (c->d_navtab) cudaFree(c->d_navtab);
+    for (auto& sl : c->slot) {
+        if (sl.done) cudaEventSynchronize(sl.done);
+        if (sl.buf) cudaFree(sl.buf);
+        for (cudaEvent_t e : { sl.in_ready, sl.in_free, sl.out_ready, sl.done }) if (e) cudaEventDestroy(e);
+    }
+    if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamDestroy(c->h2d_stream); }
         c->d_navtab = nullptr; c->navtab_doubles = 0;
         CUDA_OK(cudaMalloc(&c->d_navtab, need * sizeof(double)));
         c->navtab_doubles = need;
@@ -887,6 +902,12 @@ void octane_ctx_destroy(octane_ctx* c)
     if (c->d_its) cudaFree(c->d_its);
     if (c->d_gk) cudaFree(c->d_gk);
     if (c->d_navtab) cudaFree(c->d_navtab);
+    for (auto& sl : c->slot) {
+        if (sl.done) cudaEventSynchronize(sl.done);
+        if (sl.buf) cudaFree(sl.buf);
+        for (cudaEvent_t e : { sl.in_ready, sl.in_free, sl.out_ready, sl.done }) if (e) cudaEventDestroy(e);
+    }
+    if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamDestroy(c->h2d_stream); }
     if (c->h_its) cudaFreeHost(c->h_its);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -1570,6 +1591,123 @@ int octane_comm_rank(octane_ctx* c, int* rank, int* world)
     if (!c) return OCTANE_EINVAL;
     if (rank) *rank = c->comm.rank;
     if (world) *world = c->comm.world;
+    return OCTANE_OK;
+}
+
+// ---- pipelined host-buffer dispatcher -----------------------------------------------------------
+// The reference handles one pair per process run (src/main.cc:439 -> oct_optical_flow); reprocessing an archive or a
+// 1-minute mesoscale sequence is a loop over pairs.  For that loop the copies are the only part of a step the GPU
+// does not need to wait for: submit() enqueues copy-in -> solve -> navigation -> copy-out of one pair on three
+// streams and returns, wait() blocks until that pair's outputs are in host memory; with two slots the copies of
+// pair k+1 and k-1 run under the solve of pair k.
+namespace {
+int slot_prepare(octane_ctx* c, int k, size_t bytes)
+{
+    auto& sl = c->slot[k];
+    if (!c->h2d_stream) CUDA_OK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    if (!sl.done) {
+        CUDA_OK(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&sl.in_free, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&sl.out_ready, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    if (bytes > sl.bytes) {
+        if (sl.busy) CUDA_OK(cudaEventSynchronize(sl.done));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (sl.buf) cudaFree(sl.buf);
+        sl.buf = nullptr; sl.bytes = 0;
+        CUDA_OK(cudaMalloc(&sl.buf, bytes));
+        sl.bytes = bytes;
+    }
+    return OCTANE_OK;
+}
+}  // namespace
+
+int octane_stream_submit(octane_ctx* c, int k, const float* img1, const float* img2, const float* cth, int nx, int ny, int nc,
+                         const octane_nav* nav, double t1, double t2, const octane_params* p, float* upix, float* vpix,
+                         short* U, short* V, short* Ur, short* Vr, short* ctp)
+{
+    if (!c || (k != 0 && k != 1) || !img1 || !img2 || !nav || !p || !U || !V || !Ur || !Vr || (!upix != !vpix)) {
+        set_err("null or invalid argument");
+        return OCTANE_EINVAL;
+    }
+    if (p->doCTH && (!cth || !ctp)) { set_err("doCTH needs cth and ctp"); return OCTANE_EINVAL; }
+    if (p->first_guess || p->dosrsal) { set_err("the pipelined dispatcher takes neither a first guess nor -srsal"); return OCTANE_EINVAL; }
+    CUDA_OK(cudaSetDevice(c->device));
+    int rc = prepare(c, nx, ny, nc, *p);
+    if (rc) return rc;
+    const Level& F = c->plan.lv.back();
+    const size_t nin = (size_t)F.g.rows * nx, nown = (size_t)(F.own1 - F.own0) * nx;
+    const size_t ib = align_up(nin * nc * sizeof(float)), fb = align_up(nown * sizeof(float)), sb = align_up(nown * sizeof(short));
+    rc = slot_prepare(c, k, 2 * ib + 3 * fb + 5 * sb);
+    if (rc) return rc;
+    auto& sl = c->slot[k];
+    if (sl.busy) {                       // resubmitting a slot implies its previous pair is finished with
+        CUDA_OK(cudaEventSynchronize(sl.done));
+        sl.busy = false;
+    }
+    char* q = sl.buf;
+    float* d_i1 = (float*)q; q += ib;
+    float* d_i2 = (float*)q; q += ib;
+    float* d_u = (float*)q; q += fb;
+    float* d_v = (float*)q; q += fb;
+    float* d_cth = (float*)q; q += fb;
+    short* d_s = (short*)q;
+    const size_t sstride = sb / sizeof(short);
+    // copy-in on its own stream: runs under the solve of the pair in the other slot
+    CUDA_OK(cudaMemcpyAsync(d_i1, img1, nin * nc * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+    CUDA_OK(cudaMemcpyAsync(d_i2, img2, nin * nc * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+    if (p->doCTH) CUDA_OK(cudaMemcpyAsync(d_cth, cth, nown * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+    CUDA_OK(cudaEventRecord(sl.in_ready, c->h2d_stream));
+    // solve + navigation on the context's stream
+    begin_call(c);
+    if (c->d_scal) CUDA_OK(cudaMemsetAsync(&c->d_scal->halo_err, 0, 2 * sizeof(int), c->stream));
+    CUDA_OK(cudaStreamWaitEvent(c->stream, sl.in_ready, 0));
+    {
+        Scope total(c, CAT_TOTAL);
+        rc = ingest(c, d_i1, d_i2, nullptr, nullptr);
+        if (rc) return rc;
+        CUDA_OK(cudaEventRecord(sl.in_free, c->stream));
+        rc = run_levels(c);
+        if (rc) return rc;
+        rc = emit(c, d_u, d_v);
+        if (rc) return rc;
+    }
+    if (p->doCTH) {
+        launch_ctp_pack(d_cth, d_s + 4 * sstride, nown, p->ir == 1, c->stream);
+        c->launches++;
+    }
+    const int nrc = pix2uv_dev_rows(c, nav, t1, t2, d_u, d_v, nx, F.own0, F.own1 - F.own0, p, d_s, d_s + sstride,
+                                    d_s + 2 * sstride, d_s + 3 * sstride);
+    if (nrc < 0) return nrc;
+    CUDA_OK(cudaEventRecord(sl.out_ready, c->stream));
+    // copy-out
+    CUDA_OK(cudaStreamWaitEvent(c->copy_stream, sl.out_ready, 0));
+    short* hs[4] = { U, V, Ur, Vr };
+    for (int i = 0; i < 4; i++)
+        CUDA_OK(cudaMemcpyAsync(hs[i], d_s + i * sstride, nown * sizeof(short), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (p->doCTH) CUDA_OK(cudaMemcpyAsync(ctp, d_s + 4 * sstride, nown * sizeof(short), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (upix) {
+        CUDA_OK(cudaMemcpyAsync(upix, d_u, nown * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+        CUDA_OK(cudaMemcpyAsync(vpix, d_v, nown * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    CUDA_OK(cudaEventRecord(sl.done, c->copy_stream));
+    sl.busy = true;
+    return nrc;
+}
+
+int octane_stream_wait(octane_ctx* c, int k)
+{
+    if (!c || (k != 0 && k != 1)) { set_err("invalid argument"); return OCTANE_EINVAL; }
+    auto& sl = c->slot[k];
+    if (!sl.busy) return OCTANE_OK;
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaEventSynchronize(sl.done));
+    sl.busy = false;
+    if (c->comm.world > 1) {
+        if (c->h_scal->halo_err) { set_err("warp left the band halo: raise max_disp"); return OCTANE_EHALO; }
+        if (c->h_scal->comm_err) { set_err("a peer's partial sums did not arrive (peer-memory exchange timed out)"); return OCTANE_ECOMM; }
+    }
     return OCTANE_OK;
 }
 

@@ -54,8 +54,23 @@ def main():
     sh = [torch.zeros((own1 - own0, nx), dtype=torch.int16, device=dev) for _ in range(4)]
     ctx.oct_pix2uv_band(nav, 0.0, dt, u, v, nx, own0, own1 - own0, *sh, p)
     ctx.synchronize()
+    # the pipelined host-buffer dispatcher on the same band: two pairs in flight, outputs equal to the device path's
+    stream_equal = True
+    if not with_fg:
+        h1 = torch.empty(img1.shape, pin_memory=True).copy_(img1).numpy()
+        h2 = torch.empty(img2.shape, pin_memory=True).copy_(img2).numpy()
+        outs = [{k: torch.zeros((own1 - own0, nx), dtype=(torch.float32 if k.endswith("Pix") else torch.int16), pin_memory=True).numpy()
+                 for k in ("uPix", "vPix", "uVal", "vVal", "uVal2", "vVal2")} for _ in range(2)]
+        for k in range(3):
+            ctx.stream_submit(k % 2, h1, h2, nav, 0.0, dt, p, outs[k % 2], nx, ny)
+            if k > 0:
+                ctx.stream_wait((k - 1) % 2)
+        ctx.stream_wait(0)
+        for o in outs:
+            stream_equal = stream_equal and np.array_equal(o["uPix"], u.cpu().numpy()) and np.array_equal(o["vPix"], v.cpu().numpy()) \
+                and np.array_equal(o["uVal"], sh[0].cpu().numpy()) and np.array_equal(o["vVal2"], sh[3].cpu().numpy())
     parts = [None] * world
-    dist.all_gather_object(parts, (own0, own1, u.cpu().numpy(), v.cpu().numpy(), sh[0].cpu().numpy(), repro,
+    dist.all_gather_object(parts, (own0, own1, u.cpu().numpy(), v.cpu().numpy(), sh[0].cpu().numpy(), repro and stream_equal,
                                    list(st.cg_iterations[:st.n_solves])))
     if rank == 0:
         parts.sort(key=lambda t: t[0])

@@ -489,3 +489,43 @@ def test_pairs_in_flight_on_several_contexts_match_sequential(ctx):
             assert np.array_equal(o["s"][k].cpu().numpy(), want[key]), key
     for c in ctxs:
         c.close()
+
+
+def test_pipelined_dispatcher_matches_blocking_calls(ctx):
+    """octane_stream_submit / octane_stream_wait over a sequence of pairs, two in flight: every pair's outputs are,
+    bit for bit, what the blocking dispatcher returns for it (same kernels, only the copies overlap)."""
+    import torch
+    nx, ny, npairs = 640, 200, 5
+    xs, ys, xo, yo, dt = S.SECTORS["meso_2km"]
+    nav = ob.goes_nav(xs, ys, xo, yo)
+    p = ob.default_params(doCTH=1, kiters=3)
+    yy, xx = np.mgrid[0:ny, 0:nx].astype(np.float32)
+    cth = (7500.0 + 7400.0 * np.sin(xx / 40.0) * np.cos(yy / 30.0)).astype(np.float32)
+    pairs = [S.make_pair(nx, ny, 300 + k)[:2] for k in range(npairs)]
+    want = [ctx.oct_optical_flow(a, b, nav, 0.0, dt, p, cth=cth) for a, b in pairs]
+
+    def pinned(dtype):
+        return torch.zeros((ny, nx), dtype=dtype, pin_memory=True).numpy()
+
+    outs = [dict(uPix=pinned(torch.float32), vPix=pinned(torch.float32), uVal=pinned(torch.int16), vVal=pinned(torch.int16),
+                 uVal2=pinned(torch.int16), vVal2=pinned(torch.int16), CTP=pinned(torch.int16)) for _ in range(2)]
+    hin = [(torch.from_numpy(a).pin_memory().numpy(), torch.from_numpy(b).pin_memory().numpy()) for a, b in pairs]
+    hcth = torch.from_numpy(cth).pin_memory().numpy()
+    got = []
+    for k in range(npairs):
+        ctx.stream_submit(k % 2, hin[k][0], hin[k][1], nav, 0.0, dt, p, outs[k % 2], nx, ny, cth=hcth)
+        if k > 0:
+            ctx.stream_wait((k - 1) % 2)
+            got.append({key: val.copy() for key, val in outs[(k - 1) % 2].items()})
+    ctx.stream_wait((npairs - 1) % 2)
+    got.append({key: val.copy() for key, val in outs[(npairs - 1) % 2].items()})
+    for k in range(npairs):
+        for key in ("uPix", "vPix", "uVal", "vVal", "uVal2", "vVal2", "CTP"):
+            assert np.array_equal(got[k][key], want[k][key]), (k, key)
+    # without the pixel displacements (the reference writes them only with -pd)
+    o = {key: outs[0][key] for key in ("uVal", "vVal", "uVal2", "vVal2")}
+    ctx.stream_submit(0, hin[0][0], hin[0][1], nav, 0.0, dt, ob.default_params(kiters=3), o, nx, ny)
+    ctx.stream_wait(0)
+    assert np.array_equal(o["uVal"], want[0]["uVal"]) and np.array_equal(o["vVal2"], want[0]["vVal2"])
+    with pytest.raises(ob.OctaneError):
+        ctx.stream_submit(0, hin[0][0], hin[0][1], nav, 0.0, dt, ob.default_params(dosrsal=1), o, nx, ny, cth=hcth)
