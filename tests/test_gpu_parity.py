@@ -330,7 +330,8 @@ def test_graph_and_plain_launch_paths_agree(ctx):
     st = ctx.stats()
     ctx.set_profile(False)
     assert np.array_equal(u1, u2) and np.array_equal(v1, v2) and np.array_equal(u1, u3)
-    assert st.finest_pass1_ms > 0 and st.finest_pass2_ms > 0 and st.n_pcg_pass1 == st.n_pcg_pass2 > 0
+    # a scene this small runs every solve as ONE cooperative launch (k_pcg_coop): timed as a whole, no per-iteration figures
+    assert st.ms_pcg_pass1 > 0 and st.kernel_launches < 400 and st.finest_pass2_ms == 0
 
 
 # ---- ingest (oct_navcal_cuda) and first-guess conversion (oct_uv2pix) --------------------------
