@@ -726,11 +726,16 @@ def main():
     else:
         dom = "pcg_pass2" if st.ms_pcg_pass2 >= st.ms_pcg_pass1 else "pcg_pass1"
     ach = k2 if dom == "pcg_pass2" else k1
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            # bytes per launch from one ncu --set full capture, keyed by workload AND rank count (see the file's note)
-            traffic = json.load(f).get(args.workload, {}).get(f"n{world}", {}).get(dom)
+            # one ncu --set full capture per workload AND rank count (see the file's note); absent -> null
+            ent = json.load(f).get(args.workload, {}).get(f"n{world}", {}).get(dom)
+        if ent and "ratio_to_algorithmic" in ent:
+            traffic = ent["ratio_to_algorithmic"] * (B_PASS2 if dom == "pcg_pass2" else b1) * float(st.finest_pixels)
+            traffic_src = f"{ent['capture']}: measured DRAM bytes / algorithmic bytes of the captured launches = {ent['ratio_to_algorithmic']}"
+        elif ent:
+            traffic, traffic_src = ent["bytes"], ent["capture"]
     except Exception:
         pass
     line = {
@@ -744,7 +749,7 @@ def main():
                          else "working set of the coarse levels fits L2; inputs re-read from HBM each step"},
         "clocks": clocks, "gpu_launches": launches * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
+                     "frac": ach / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": (B_PASS2 if dom == "pcg_pass2" else b1) * float(st.finest_pixels),
                      "peak_source": peak_src,
                      "bytes_per_pixel_per_launch": B_PASS2 if dom == "pcg_pass2" else b1,
