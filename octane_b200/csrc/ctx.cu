@@ -248,8 +248,7 @@ size_t arena_layout(const Plan& pl, Buffers* b, char* base)
     B.pcg.ru = take(P); B.pcg.rv = take(P); B.pcg.xu = take(P); B.pcg.xv = take(P);
     B.pcg.pu[0] = take(P); B.pcg.pu[1] = take(P); B.pcg.pv[0] = take(P); B.pcg.pv[1] = take(P);
     B.pcg.qu = take(P); B.pcg.qv = take(P);
-    B.pcg.q2u = take(P); B.pcg.q2v = take(P);
-    B.pcg.r2u = B.pcg.pu[1]; B.pcg.r2v = B.pcg.pv[1];     // the merged-reduction solver keeps p in pu[0] / pv[0] only
+    B.pcg.r2u = B.pcg.qu; B.pcg.r2v = B.pcg.qv;           // the merged-reduction solver never stores q: r's second buffer
     return off;
 }
 
@@ -323,12 +322,8 @@ int prepare(octane_ctx* c, int nx, int ny, int nc, const octane_params& p)
                 else { pl.lv[k].dn_ru = bn.pcg.ru + shift; pl.lv[k].dn_rv = bn.pcg.rv + shift; }
                 FusedPeers& fp = pl.lv[k].fp;
                 float* rb[2][2] = { { bn.pcg.ru, bn.pcg.rv }, { bn.pcg.r2u, bn.pcg.r2v } };
-                float* qb[2][2] = { { bn.pcg.qu, bn.pcg.qv }, { bn.pcg.q2u, bn.pcg.q2v } };
                 for (int bi = 0; bi < 2; bi++)
-                    for (int ci = 0; ci < 2; ci++) {
-                        (side == 0 ? fp.up_r : fp.dn_r)[bi][ci] = rb[bi][ci] + shift;
-                        (side == 0 ? fp.up_q : fp.dn_q)[bi][ci] = qb[bi][ci] + shift;
-                    }
+                    for (int ci = 0; ci < 2; ci++) (side == 0 ? fp.up_r : fp.dn_r)[bi][ci] = rb[bi][ci] + shift;
             }
         }
     }
@@ -741,15 +736,15 @@ int pix2uv_dev_rows(octane_ctx* c, const octane_nav* nav, double t1, double t2, 
     return OCTANE_OK;
 }
 
-// algorithmic bytes per pixel of one merged-reduction launch: r, q, p in and out, x in and out
+// algorithmic bytes per pixel of one merged-reduction launch: r, p in and out, x in and out
 // every second iteration, the five coefficient planes (three when W = N = -1 is known)
 double fused_bytes(int ki, bool cwn)
 {
     const double coef = cwn ? 12.0 : 20.0;
     if (ki < 0) return 8.0 + coef;                       // r + coefficients, nothing written
-    if (ki == 0) return 8.0 + coef + 24.0;               // no p, q of a previous iteration yet
-    if (ki == 1) return 24.0 + coef + 32.0;              // x is started, not read
-    return (ki & 1) ? 32.0 + coef + 32.0 : 24.0 + coef + 24.0;
+    if (ki == 0) return 8.0 + coef + 16.0;               // no p of a previous iteration yet; r, p written
+    if (ki == 1) return 16.0 + coef + 24.0;              // x is started, not read
+    return (ki & 1) ? 24.0 + coef + 24.0 : 16.0 + coef + 16.0;
 }
 
 void collect_stats(octane_ctx* c)

@@ -33,9 +33,10 @@ struct PcgBuffers {
     float *xu, *xv;            // solution increment
     float *pu[2], *pv[2];      // search direction, ping-pong
     float *qu, *qv;            // A p
-    // merged-reduction solver (pcg_fused.cu): r and q are read with row halos and rewritten by the same launch,
-    // so each has a second buffer (r2 aliases pu[1] / pv[1], which that solver does not use; q2 is its own)
-    float *r2u, *r2v, *q2u, *q2v;
+    // merged-reduction solver (pcg_fused.cu): r and p are read with row halos and rewritten by the same launch, so
+    // both are double-buffered: p in pu[] / pv[] as for the two-pass kernels, r's second buffer in the planes of q
+    // (that solver computes q = A p on the fly and never stores it)
+    float *r2u, *r2v;
     PcgScalars* scal;          // device
     double* partials;          // device, >= 4 * max blocks
     unsigned* ticket;          // device
@@ -90,13 +91,13 @@ void launch_update_uv(float* u, float* v, const PcgBuffers& b, const Geom& g, in
                       int* its_out, int sm_count, cudaStream_t st);
 // ---- pcg_fused.cu: one launch and one reduction per iteration (merged recurrence; large levels)
 bool pcg_fused_usable(const Geom& g, int nrows);
-// banded runs: the neighbours' r / q buffers [buffer][component] as mapped here (peer memory), shifted to this rank's
+// banded runs: the neighbours' two r buffers [buffer][component] as mapped here (peer memory), shifted to this rank's
 // row origin; all nullptr on one GPU and at the outer edges
 struct FusedPeers {
-    float *up_r[2][2], *up_q[2][2], *dn_r[2][2], *dn_q[2][2];
+    float *up_r[2][2], *dn_r[2][2];
 };
-// ki = -1: forms the first alpha (w0 = A z0, no writes); ki >= 0: iteration ki.  Reads r[ki & 1], q[ki & 1]
-// (r[0] = ru / rv as the build leaves it), writes the other buffer of each pair; p = pu[0] / pv[0] in place.
+// ki = -1: forms the first alpha (q0 = A z0, no writes); ki >= 0: iteration ki.  Reads r[ki & 1], p[ki & 1]
+// (r[0] = ru / rv as the build leaves it), writes the other buffer of each pair.
 void launch_pcg_fused(const PcgBuffers& b, const Geom& g, int ja, int jb, int ki, const FusedPeers& peers,
                       int sm_count, cudaStream_t st, int const_wn);
 // u += x (+ the pending alpha p when the iteration count is odd), after a merged-reduction solve

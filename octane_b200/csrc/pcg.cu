@@ -457,7 +457,8 @@ k_update_uv(float* __restrict__ u, float* __restrict__ v, PcgBuffers b, Geom g, 
 
 // The same after a merged-reduction solve (pcg_fused.cu): x is brought up to date every second iteration (two terms
 // at once), so after an odd number of iterations the last term alpha p is still pending; x exists from the
-// second iteration on and p is single-buffered (pu[0] / pv[0]).
+// second iteration on; iteration k leaves its p in pu[(k & 1) ^ 1], so the last one is in pu[its & 1] as for the
+// two-pass kernels.
 __global__ void __launch_bounds__(256)
 k_update_uv_fused(float* __restrict__ u, float* __restrict__ v, PcgBuffers b, Geom g, int ja, int jb, int* its_out)
 {
@@ -476,7 +477,7 @@ k_update_uv_fused(float* __restrict__ u, float* __restrict__ v, PcgBuffers b, Ge
         float4 a = ld4(u + off), c = ld4(v + off);
         float4 xu = make_float4(0.f, 0.f, 0.f, 0.f), xv = xu, p_u = xu, p_v = xu;
         if (havex) { xu = ld4(b.xu + off); xv = ld4(b.xv + off); }
-        if (pending) { p_u = ld4(b.pu[0] + off); p_v = ld4(b.pv[0] + off); }
+        if (pending) { p_u = ld4(b.pu[its & 1] + off); p_v = ld4(b.pv[its & 1] + off); }
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (i0 + k < g.nx) {

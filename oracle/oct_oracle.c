@@ -459,9 +459,9 @@ int oracle_pcg(const float *coef, float *bu, float *bv, float *xu, float *xv,
 }
 
 /* ---- model of the product's single-reduction PCG (octane_b200/csrc/pcg_fused.cu) ------------------
- * NOT a restatement of the reference: the same Krylov iterate as oracle_pcg in exact arithmetic, computed with the
- * merged-reduction recurrences (w = A z, q = w + beta q instead of q = A p; one dot-product phase per iteration:
- * r.z, r.r, z.w, z.q, p.w, p.q), scalars in double, vectors in float.  It exists so that the distance between
+ * NOT a restatement of the reference: the same vector recurrences as oracle_pcg (p = z + beta p, q = A p,
+ * x += alpha p, r -= alpha q) with the scalars of the NEXT iteration formed in one dot-product phase from
+ * r.z, r.r, z.w, z.q, p.w, p.q (w = A z of the new residual), scalars in double, vectors in float.  It exists so that the distance between
  * the two recurrences can be measured on the CPU (tests/test_oracle_golden.py) and so that the CUDA kernel has a
  * model with the same operation order.  Selected with oracle_set_solver(1); the default (0) is the reference's
  * recurrence, which every parity gate is judged against. */
@@ -494,10 +494,12 @@ int oracle_pcg_merged(const float *coef, float *bu, float *bv, float *xu, float 
     while ((rr > tol) && (ki < iters)) {
         const float af = (float)alpha, bf = (float)beta, naf = -af;
         for (size_t i = 0; i < n; i++) {
-            pu[i] = fmaf(bf, pu[i], zu[i]);  pv[i] = fmaf(bf, pv[i], zv[i]);      /* p = z + beta p */
-            qu[i] = fmaf(bf, qu[i], wu[i]);  qv[i] = fmaf(bf, qv[i], wv[i]);      /* q = w + beta q  (= A p) */
-            xu[i] = fmaf(af, pu[i], xu[i]);  xv[i] = fmaf(af, pv[i], xv[i]);
-            ru[i] = fmaf(naf, qu[i], ru[i]); rv[i] = fmaf(naf, qv[i], rv[i]);
+            pu[i] = fmaf(bf, pu[i], zu[i]);  pv[i] = fmaf(bf, pv[i], zv[i]);      /* p = z + beta p, :1146 */
+            xu[i] = fmaf(af, pu[i], xu[i]);  xv[i] = fmaf(af, pv[i], xv[i]);      /* :1172 */
+        }
+        oracle_apply(coef, pu, pv, xi, yi, qu, qv);                                /* q = A p, :1161 */
+        for (size_t i = 0; i < n; i++) {
+            ru[i] = fmaf(naf, qu[i], ru[i]); rv[i] = fmaf(naf, qv[i], rv[i]);     /* :1174 */
             zu[i] = mu[i] * ru[i];           zv[i] = mv[i] * rv[i];
         }
         oracle_apply(coef, zu, zv, xi, yi, wu, wv);
