@@ -69,9 +69,28 @@ def main():
         for o in outs:
             stream_equal = stream_equal and np.array_equal(o["uPix"], u.cpu().numpy()) and np.array_equal(o["vPix"], v.cpu().numpy()) \
                 and np.array_equal(o["uVal"], sh[0].cpu().numpy()) and np.array_equal(o["vVal2"], sh[3].cpu().numpy())
+    # OCTANE_EHALO is not sticky: a halo sized for a displacement bound that is too small fails on the ranks whose warp
+    # leaves the band, and the SAME context solves again after the caller raised max_disp (a collective re-plan)
+    halo_recovers = True
+    if not with_fg:
+        tight = ob.default_params(max_disp=0)
+        o0, o1, i0, i1 = ob.band_plan(nx, ny, tight, rank, world)
+        t1_, t2_ = S.make_pair_torch(nx, ny, 9, dev, rows=(i0, i1), drift=(0.8, -9.0))     # 9 px of vertical motion
+        ut = torch.zeros((o1 - o0, nx), device=dev); vt = torch.zeros_like(ut)
+        failed = 0
+        try:
+            ctx.oct_variational_optical_flow_band(t1_, t2_, ut, vt, nx, ny, tight)
+        except ob.OctaneError as e:
+            failed = int(e.code == -5)
+        flags = [None] * world
+        dist.all_gather_object(flags, failed)
+        u3 = torch.zeros_like(u); v3 = torch.zeros_like(v)
+        ctx.oct_variational_optical_flow_band(img1, img2, u3, v3, nx, ny, p)               # the original plan again: must succeed
+        ctx.synchronize()
+        halo_recovers = any(flags) and bool(torch.equal(u3, u) and torch.equal(v3, v))
     parts = [None] * world
-    dist.all_gather_object(parts, (own0, own1, u.cpu().numpy(), v.cpu().numpy(), sh[0].cpu().numpy(), repro and stream_equal,
-                                   list(st.cg_iterations[:st.n_solves])))
+    dist.all_gather_object(parts, (own0, own1, u.cpu().numpy(), v.cpu().numpy(), sh[0].cpu().numpy(),
+                                   repro and stream_equal and halo_recovers, list(st.cg_iterations[:st.n_solves])))
     if rank == 0:
         parts.sort(key=lambda t: t[0])
         U = np.concatenate([t[2] for t in parts]); V = np.concatenate([t[3] for t in parts])
