@@ -14,6 +14,9 @@
 namespace octane {
 
 #define BUILD_ROWS 64
+#ifndef OCTANE_BUILD_OCC
+#define OCTANE_BUILD_OCC 3      // resident blocks of 256 threads per SM the register allocation aims at
+#endif
 
 __device__ __forceinline__ float jsq(float x) { return x * x; }
 
@@ -297,7 +300,7 @@ void launch_build(const LevelFields& f, const PcgBuffers& b, const Geom& g, int 
                   const BuildParams& bp, int halo_check, cudaStream_t st)
 {
     dim3 grid((g.nx + 31) / 32, (jb - ja + BUILD_ROWS - 1) / BUILD_ROWS), block(32, 8);
-#define LAUNCH_BUILD(MODE) k_build<MODE, 3><<<grid, block, 0, st>>>(f, b, g, ja, jb, da, db, bp, halo_check)
+#define LAUNCH_BUILD(MODE) k_build<MODE, OCTANE_BUILD_OCC><<<grid, block, 0, st>>>(f, b, g, ja, jb, da, db, bp, halo_check)
     if (bp.al1 == 1.0)      LAUNCH_BUILD(GNC_QUADRATIC);
     else if (bp.al1 == 0.0) LAUNCH_BUILD(GNC_ROBUST);
     else                    LAUNCH_BUILD(GNC_BLEND);
