@@ -624,12 +624,17 @@ def main():
         outs = [{k: torch.zeros((nown, nx), dtype=(torch.float32 if k.endswith("Pix") else torch.int16), pin_memory=True).numpy()
                  for k in ("uPix", "vPix", "uVal", "vVal", "uVal2", "vVal2")} for _ in range(2)]
         state = {"k": 0}
+        host = {"submit": 0.0, "wait": 0.0, "n": 0}      # host time inside the two calls (ms): submit must not block
 
         def submit_next():
             k = state["k"]
+            t0 = time.perf_counter()
             ctx.stream_submit(k % 2, n1, n2, nav, 0.0, dt, p, outs[k % 2], nx, ny)
+            t1 = time.perf_counter()
             if k > 0:
                 ctx.stream_wait((k - 1) % 2)
+            t2 = time.perf_counter()
+            host["submit"] += (t1 - t0) * 1e3; host["wait"] += (t2 - t1) * 1e3; host["n"] += 1
             state["k"] = k + 1
 
         def drain():
@@ -655,6 +660,7 @@ def main():
         for _ in range(max(2, min(args.warmup, 3))):
             submit_next()
         drain()
+        host.update(submit=0.0, wait=0.0, n=0)
         ms_e2e = pipelined(args.steps)
         # per-pair latency: one pair at a time through the same entry points
         def one():
@@ -665,6 +671,7 @@ def main():
                "h2d_bytes_per_step": 2 * nx * nin * 4, "d2h_bytes_per_step": nx * nown * (2 * 4 + 4 * 2),
                "api": "octane_stream_submit / octane_stream_wait (pinned host buffers; two pairs in flight: the copies of one "
                       "pair run under the solve of the other; every pair's H2D and D2H are inside the timed region)",
+               "host_ms_in_submit": host["submit"] / max(host["n"], 1), "host_ms_in_wait": host["wait"] / max(host["n"], 1),
                "latency_ms_per_pair": ms_lat, "latency_Mpix/s": mpix / (ms_lat / 1e3),
                "latency_api": "one pair at a time: submit + wait (copy-in, solve, navigation, copy-out in sequence)"}
         if world == 1:

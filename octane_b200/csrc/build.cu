@@ -15,7 +15,8 @@ namespace octane {
 
 #define BUILD_ROWS 64
 #ifndef OCTANE_BUILD_OCC
-#define OCTANE_BUILD_OCC 3      // resident blocks of 256 threads per SM the register allocation aims at
+#define OCTANE_BUILD_OCC 4      // resident blocks of 256 threads per SM the register allocation aims at (64 registers,
+                                // no spills; measured 2 / 3 / 4: profiles/r02_build_occ_ab.txt)
 #endif
 
 __device__ __forceinline__ float jsq(float x) { return x * x; }

@@ -90,15 +90,16 @@ namespace {
 // every rank contributes `bytes` bytes; out (host) receives world * bytes
 int allgather_bytes(Comm* c, const void* mine, size_t bytes, void* out, cudaStream_t st)
 {
-    char* d = nullptr;
-    if (cudaMalloc(&d, bytes * (c->world + 1)) != cudaSuccess) { snprintf(errbuf, sizeof errbuf, "cudaMalloc (allgather)"); return -1; }
+    const size_t stage_bytes = 17 * sizeof(cudaIpcMemHandle_t);     // the largest item exchanged, 16 ranks + own
+    if (bytes * (c->world + 1) > stage_bytes) { snprintf(errbuf, sizeof errbuf, "allgather item too large"); return -1; }
+    if (!c->d_stage && cudaMalloc(&c->d_stage, stage_bytes) != cudaSuccess) { snprintf(errbuf, sizeof errbuf, "cudaMalloc (allgather)"); return -1; }
+    char* d = c->d_stage;
     int rc = 0;
     if (cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
     if (!rc) rc = check(api.AllGather(d, d + bytes, bytes, ncclChar, (ncclComm_t)c->nccl_comm, st), "ncclAllGather");
     if (!rc && cudaMemcpyAsync(out, d + bytes, bytes * c->world, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
     if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = -1;
     if (rc && !errbuf[0]) snprintf(errbuf, sizeof errbuf, "allgather of IPC handles failed");
-    cudaFree(d);
     return rc;
 }
 
@@ -157,12 +158,14 @@ int comm_p2p_unmap_arenas(Comm* c, cudaStream_t st)
     return all_ok(c, 1, st) < 0 ? -1 : 0;                  // barrier: nobody frees a workspace a peer still maps
 }
 
-int comm_p2p_map_arenas(Comm* c, void* my_arena, cudaStream_t st)
+int comm_p2p_map_arenas(Comm* c, void* my_arena, int local_ok, cudaStream_t st)
 {
     if (!c->p2p) return 0;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof mine);
-    int ok = cudaIpcGetMemHandle(&mine, my_arena) == cudaSuccess;
+    // a rank whose own preparation failed (local_ok == 0) still takes part in both exchanges
+    // and votes "no": its peers get an error instead of waiting for it forever
+    int ok = local_ok && my_arena && cudaIpcGetMemHandle(&mine, my_arena) == cudaSuccess;
     std::vector<cudaIpcMemHandle_t> all(c->world);
     if (allgather_bytes(c, &mine, sizeof mine, all.data(), st)) return -1;
     const int nb[2] = { c->rank - 1, c->rank + 1 };
@@ -190,6 +193,8 @@ void comm_destroy(Comm* c)
     if (c->window) cudaFree(c->window);
     if (c->d_peers) cudaFree(c->d_peers);
     if (c->d_epoch) cudaFree(c->d_epoch);
+    if (c->d_stage) cudaFree(c->d_stage);
+    c->d_stage = nullptr;
     c->window = nullptr; c->d_peers = nullptr; c->d_epoch = nullptr; c->p2p = false;
     if (c->nccl_comm && api.CommDestroy) api.CommDestroy((ncclComm_t)c->nccl_comm);
     c->nccl_comm = nullptr;
@@ -211,17 +216,23 @@ int comm_halo_exchange(Comm* c, int nplanes, float* const* send_up, float* const
     ncclComm_t comm = (ncclComm_t)c->nccl_comm;
     const int up = c->rank - 1, dn = c->rank + 1;
     if (check(api.GroupStart(), "ncclGroupStart")) return -1;
-    for (int p = 0; p < nplanes; p++) {
+    int rc = 0;
+    for (int p = 0; p < nplanes && !rc; p++) {
         if (up >= 0) {
-            if (check(api.Send(send_up[p], count, ncclFloat32, up, comm, st), "ncclSend")) return -1;
-            if (check(api.Recv(recv_up[p], count, ncclFloat32, up, comm, st), "ncclRecv")) return -1;
+            rc = check(api.Send(send_up[p], count, ncclFloat32, up, comm, st), "ncclSend");
+            if (!rc) rc = check(api.Recv(recv_up[p], count, ncclFloat32, up, comm, st), "ncclRecv");
         }
-        if (dn < c->world) {
-            if (check(api.Send(send_dn[p], count, ncclFloat32, dn, comm, st), "ncclSend")) return -1;
-            if (check(api.Recv(recv_dn[p], count, ncclFloat32, dn, comm, st), "ncclRecv")) return -1;
+        if (!rc && dn < c->world) {
+            rc = check(api.Send(send_dn[p], count, ncclFloat32, dn, comm, st), "ncclSend");
+            if (!rc) rc = check(api.Recv(recv_dn[p], count, ncclFloat32, dn, comm, st), "ncclRecv");
         }
     }
-    return check(api.GroupEnd(), "ncclGroupEnd");
+    // the group is always closed, also after a failed call inside it (the first error is the one reported)
+    char first[sizeof errbuf];
+    memcpy(first, errbuf, sizeof errbuf);
+    const int rc_end = check(api.GroupEnd(), "ncclGroupEnd");
+    if (rc) { memcpy(errbuf, first, sizeof errbuf); return -1; }
+    return rc_end;
 }
 
 }  // namespace octane

@@ -21,6 +21,8 @@ struct Comm {
     void** d_peers = nullptr;            // device copy of peer_window
     unsigned* d_epoch = nullptr;         // device [3]
     void* nb_arena[2] = { nullptr, nullptr };   // rank-1 / rank+1 workspace as mapped here
+    char* d_stage = nullptr;             // staging for the small host-side exchanges (allocated once: a re-plan under
+                                         // memory pressure must not fail to allocate it on one rank only)
 };
 
 int comm_unique_id(char id[128]);
@@ -40,7 +42,7 @@ int comm_p2p_init(Comm* c, size_t window_bytes, cudaStream_t st);
 // Collective, call when the workspace (re)appears: unmap the neighbours' old workspaces
 // (comm_p2p_unmap_arenas, before anybody frees), then map the new ones.
 int comm_p2p_unmap_arenas(Comm* c, cudaStream_t st);
-int comm_p2p_map_arenas(Comm* c, void* my_arena, cudaStream_t st);
+int comm_p2p_map_arenas(Comm* c, void* my_arena, int local_ok, cudaStream_t st);
 const char* comm_last_error();
 
 }  // namespace octane

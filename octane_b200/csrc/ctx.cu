@@ -206,6 +206,7 @@ struct octane_ctx {
         bool busy = false;
     } slot[2];
     cudaStream_t h2d_stream = nullptr;
+    int copy_prio = 0;
     // host-API staging (device)
     char* stage = nullptr;
     size_t stage_bytes = 0;
@@ -285,39 +286,57 @@ int prepare(octane_ctx* c, int nx, int ny, int nc, const octane_params& p)
     c->plan_valid = false;
     destroy_graphs(c);
     Plan pl;
-    int rc = make_plan(pl, nx, ny, nc, p, c->comm.rank, c->comm.world);
-    if (rc) return rc;
-    const size_t need = arena_layout(pl, nullptr, nullptr);
     const bool p2p = c->comm.world > 1 && c->comm.p2p;
+    // With a peer-memory communicator a re-plan is collective (every rank re-plans at the same
+    // call) and every rank must reach the exchanges inside comm_p2p_unmap_arenas and
+    // comm_p2p_map_arenas: a rank-local failure (a refused plan, no memory, a CUDA error) is
+    // carried in `local` and voted on in the mapping step, never returned before it -- the
+    // peers would wait for this rank forever.
+    int local = make_plan(pl, nx, ny, nc, p, c->comm.rank, c->comm.world);
+    if (local && !p2p) return local;
+    const size_t need = local ? 0 : arena_layout(pl, nullptr, nullptr);
     if (p2p) {
-        // collective (every rank re-plans at the same call): nobody may free a workspace a peer still maps
-        CUDA_OK(cudaStreamSynchronize(c->stream));
+        // nobody may free a workspace a peer still maps
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess && !local) { set_err("cudaStreamSynchronize (re-plan)"); local = OCTANE_ECUDA; }
         if (comm_p2p_unmap_arenas(&c->comm, c->stream)) { set_err("%s", comm_last_error()); return OCTANE_ECOMM; }
     }
-    if (need > c->arena_bytes) {
-        CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (!local && need > c->arena_bytes) {
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { set_err("cudaStreamSynchronize (workspace)"); local = OCTANE_ECUDA; }
         if (c->arena) cudaFree(c->arena);
         c->arena = nullptr; c->arena_bytes = 0;
-        CUDA_OK(cudaMalloc(&c->arena, need));
-        c->arena_bytes = need;
+        if (local) {
+        } else if (cudaMalloc(&c->arena, need) != cudaSuccess) {
+            cudaGetLastError();
+            c->arena = nullptr;
+            set_err("cudaMalloc (workspace): out of device memory");
+            local = OCTANE_ENOMEM;
+        } else c->arena_bytes = need;
     }
     // padding columns / halo rows must hold finite values (they are multiplied by zero
     // coefficients): clear the whole workspace once per plan
-    CUDA_OK(cudaMemsetAsync(c->arena, 0, need, c->stream));
-    arena_layout(pl, &c->buf, c->arena);
+    if (!local && cudaMemsetAsync(c->arena, 0, need, c->stream) != cudaSuccess) { set_err("cudaMemsetAsync (workspace)"); local = OCTANE_ECUDA; }
+    if (!local) arena_layout(pl, &c->buf, c->arena);
+    Plan pn[2];
     if (p2p) {
-        CUDA_OK(cudaStreamSynchronize(c->stream));           // the clear must not race a neighbour's first halo store
-        if (comm_p2p_map_arenas(&c->comm, c->arena, c->stream)) { set_err("%s", comm_last_error()); return OCTANE_ECOMM; }
+        for (int side = 0; side < 2 && !local; side++) {
+            const int nb = c->comm.rank + (side == 0 ? -1 : 1);
+            if (nb >= 0 && nb < c->comm.world) local = make_plan(pn[side], nx, ny, nc, p, nb, c->comm.world);
+        }
+        // the clear must not race a neighbour's first halo store
+        if (!local && cudaStreamSynchronize(c->stream) != cudaSuccess) { set_err("cudaStreamSynchronize (workspace)"); local = OCTANE_ECUDA; }
+        if (comm_p2p_map_arenas(&c->comm, c->arena, local == OCTANE_OK, c->stream)) {
+            if (!local) { set_err("%s", comm_last_error()); local = OCTANE_ECOMM; }
+        }
+    }
+    if (local) return local;
+    if (p2p) {
         for (int side = 0; side < 2; side++) {
             const int nb = c->comm.rank + (side == 0 ? -1 : 1);
             if (nb < 0 || nb >= c->comm.world) continue;
-            Plan pn;
-            rc = make_plan(pn, nx, ny, nc, p, nb, c->comm.world);
-            if (rc) return rc;
             Buffers bn;
-            arena_layout(pn, &bn, (char*)c->comm.nb_arena[side]);
+            arena_layout(pn[side], &bn, (char*)c->comm.nb_arena[side]);
             for (size_t k = 0; k < pl.lv.size(); k++) {
-                const long long shift = (long long)(pl.lv[k].g.j0 - pn.lv[k].g.j0) * pl.lv[k].g.pitch;
+                const long long shift = (long long)(pl.lv[k].g.j0 - pn[side].lv[k].g.j0) * pl.lv[k].g.pitch;
                 if (side == 0) { pl.lv[k].up_ru = bn.pcg.ru + shift; pl.lv[k].up_rv = bn.pcg.rv + shift; }
                 else { pl.lv[k].dn_ru = bn.pcg.ru + shift; pl.lv[k].dn_rv = bn.pcg.rv + shift; }
                 FusedPeers& fp = pl.lv[k].fp;
@@ -332,7 +351,7 @@ int prepare(octane_ctx* c, int nx, int ny, int nc, const octane_params& p)
     int bb = build_partial_blocks(F.g, F.g.rows);
     for (auto& L : pl.lv) { int t = build_partial_blocks(L.g, L.g.rows); if (t > bb) bb = t; }
     if (bb > pb) pb = bb;
-    rc = ensure_small(c, pb);
+    int rc = ensure_small(c, pb);
     if (rc) return rc;
     c->buf.pcg.scal = c->d_scal;
     c->buf.pcg.partials = c->d_partials;
@@ -718,12 +737,6 @@ int pix2uv_dev_rows(octane_ctx* c, const octane_nav* nav, double t1, double t2, 
     if (need > c->navtab_doubles) {
         CUDA_OK(cudaStreamSynchronize(c->stream));
         if (c->d_navtab) cudaFree(c->d_navtab);
-    for (auto& sl : c->slot) {
-        if (sl.done) cudaEventSynchronize(sl.done);
-        if (sl.buf) cudaFree(sl.buf);
-        for (cudaEvent_t e : { sl.in_ready, sl.in_free, sl.out_ready, sl.done }) if (e) cudaEventDestroy(e);
-    }
-    if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamDestroy(c->h2d_stream); }
         c->d_navtab = nullptr; c->navtab_doubles = 0;
         CUDA_OK(cudaMalloc(&c->d_navtab, need * sizeof(double)));
         c->navtab_doubles = need;
@@ -868,7 +881,12 @@ int octane_ctx_create(octane_ctx** out, int device)
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_err("cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return OCTANE_ECUDA; }
-    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // developer switch (timing experiments): the copy streams at the highest stream priority
+    const bool prio = getenv("OCTANE_COPY_PRIO") && atoi(getenv("OCTANE_COPY_PRIO")) != 0;
+    int plo = 0, phi = 0;
+    cudaDeviceGetStreamPriorityRange(&plo, &phi);
+    c->copy_prio = prio ? phi : 0;
+    if (cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, c->copy_prio) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
         set_err("cudaStreamCreate (copy stream)");
         cudaStreamDestroy(c->stream);
@@ -1599,7 +1617,7 @@ namespace {
 int slot_prepare(octane_ctx* c, int k, size_t bytes)
 {
     auto& sl = c->slot[k];
-    if (!c->h2d_stream) CUDA_OK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    if (!c->h2d_stream) CUDA_OK(cudaStreamCreateWithPriority(&c->h2d_stream, cudaStreamNonBlocking, c->copy_prio));
     if (!sl.done) {
         CUDA_OK(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&sl.in_free, cudaEventDisableTiming));
@@ -1649,9 +1667,13 @@ int octane_stream_submit(octane_ctx* c, int k, const float* img1, const float* i
     float* d_cth = (float*)q; q += fb;
     short* d_s = (short*)q;
     const size_t sstride = sb / sizeof(short);
+    // developer switch for timing experiments only (results are then stale): 1 = skip copy-in, 2 = skip copy-out
+    static const int skip = getenv("OCTANE_STREAM_SKIP") ? atoi(getenv("OCTANE_STREAM_SKIP")) : 0;
     // copy-in on its own stream: runs under the solve of the pair in the other slot
+    if (!(skip & 1)) {
     CUDA_OK(cudaMemcpyAsync(d_i1, img1, nin * nc * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
     CUDA_OK(cudaMemcpyAsync(d_i2, img2, nin * nc * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+    }
     if (p->doCTH) CUDA_OK(cudaMemcpyAsync(d_cth, cth, nown * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
     CUDA_OK(cudaEventRecord(sl.in_ready, c->h2d_stream));
     // solve + navigation on the context's stream
@@ -1679,10 +1701,10 @@ int octane_stream_submit(octane_ctx* c, int k, const float* img1, const float* i
     // copy-out
     CUDA_OK(cudaStreamWaitEvent(c->copy_stream, sl.out_ready, 0));
     short* hs[4] = { U, V, Ur, Vr };
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 4 && !(skip & 2); i++)
         CUDA_OK(cudaMemcpyAsync(hs[i], d_s + i * sstride, nown * sizeof(short), cudaMemcpyDeviceToHost, c->copy_stream));
     if (p->doCTH) CUDA_OK(cudaMemcpyAsync(ctp, d_s + 4 * sstride, nown * sizeof(short), cudaMemcpyDeviceToHost, c->copy_stream));
-    if (upix) {
+    if (upix && !(skip & 2)) {
         CUDA_OK(cudaMemcpyAsync(upix, d_u, nown * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
         CUDA_OK(cudaMemcpyAsync(vpix, d_v, nown * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
     }

@@ -88,9 +88,41 @@ def main():
         ctx.oct_variational_optical_flow_band(img1, img2, u3, v3, nx, ny, p)               # the original plan again: must succeed
         ctx.synchronize()
         halo_recovers = any(flags) and bool(torch.equal(u3, u) and torch.equal(v3, v))
+    # a re-plan that fails on ONE rank (no device memory for the larger workspace) must come back as an error on every
+    # rank -- the failing rank votes in the workspace-mapping exchange instead of leaving it -- and the context must
+    # solve again afterwards
+    replan_recovers = True
+    if not with_fg and world > 1:
+        ny2 = 3 * ny                           # a workspace three times the current one ...
+        o0, o1, i0, i1 = ob.band_plan(nx, ny2, p, rank, world)
+        b1, b2 = S.make_pair_torch(nx, ny2, 9, dev, rows=(i0, i1))
+        ub = torch.zeros((o1 - o0, nx), device=dev); vb = torch.zeros_like(ub)
+        hog = None
+        if rank == world - 1:                  # ... cannot be allocated on the last rank: 8 MiB + the old one are free
+            torch.cuda.synchronize(dev)
+            torch.cuda.empty_cache()
+            free, _ = torch.cuda.mem_get_info(dev)
+            hog = torch.empty(max(free - (8 << 20), 0), dtype=torch.uint8, device=dev)
+        code = 0
+        try:
+            ctx.oct_variational_optical_flow_band(b1, b2, ub, vb, nx, ny2, p)
+            ctx.synchronize()
+        except ob.OctaneError as e:
+            code = e.code
+        codes = [None] * world
+        dist.all_gather_object(codes, code)
+        del hog, b1, b2, ub, vb
+        torch.cuda.empty_cache()
+        u4 = torch.zeros_like(u); v4 = torch.zeros_like(v)
+        ctx.oct_variational_optical_flow_band(img1, img2, u4, v4, nx, ny, p)
+        ctx.synchronize()
+        replan_recovers = (codes[world - 1] == -3 and all(c_ != 0 for c_ in codes)
+                           and bool(torch.equal(u4, u) and torch.equal(v4, v)))
+        if not replan_recovers:
+            print(f"REPLAN rank {rank}: codes {codes}", flush=True)
     parts = [None] * world
     dist.all_gather_object(parts, (own0, own1, u.cpu().numpy(), v.cpu().numpy(), sh[0].cpu().numpy(),
-                                   repro and stream_equal and halo_recovers, list(st.cg_iterations[:st.n_solves])))
+                                   repro and stream_equal and halo_recovers and replan_recovers, list(st.cg_iterations[:st.n_solves])))
     if rank == 0:
         parts.sort(key=lambda t: t[0])
         U = np.concatenate([t[2] for t in parts]); V = np.concatenate([t[3] for t in parts])

@@ -530,3 +530,36 @@ def test_pipelined_dispatcher_matches_blocking_calls(ctx):
     assert np.array_equal(o["uVal"], want[0]["uVal"]) and np.array_equal(o["vVal2"], want[0]["vVal2"])
     with pytest.raises(ob.OctaneError):
         ctx.stream_submit(0, hin[0][0], hin[0][1], nav, 0.0, dt, ob.default_params(dosrsal=1), o, nx, ny, cth=hcth)
+
+
+def test_fresh_context_first_call_is_the_pipelined_dispatcher():
+    """A context whose very first call is octane_stream_submit (navigation tables, staging slots and the copy-in stream are
+    all created inside it), then a larger scene through the same context while the other slot is still in flight:
+    nothing a live slot uses may be released by that growth."""
+    import torch
+    xs, ys, xo, yo, dt = S.SECTORS["meso_2km"]
+    nav = ob.goes_nav(xs, ys, xo, yo)
+    p = ob.default_params(kiters=3)
+    sizes = [(640, 200), (704, 320)]
+    pairs = [S.make_pair(nx, ny, 410 + i)[:2] for i, (nx, ny) in enumerate(sizes)]
+    ref = ob.Context(0)
+    try:
+        want = [ref.oct_optical_flow(a, b, nav, 0.0, dt, p) for a, b in pairs]
+    finally:
+        ref.close()
+    c = ob.Context(0)
+    try:
+        outs, keep = [], []
+        for i, (nx, ny) in enumerate(sizes):
+            o = {k: torch.zeros((ny, nx), dtype=(torch.float32 if k.endswith("Pix") else torch.int16), pin_memory=True).numpy()
+                 for k in ("uPix", "vPix", "uVal", "vVal", "uVal2", "vVal2")}
+            a, b = (torch.from_numpy(x).pin_memory().numpy() for x in pairs[i])
+            keep.append((a, b))
+            c.stream_submit(i, a, b, nav, 0.0, dt, p, o, nx, ny)      # slot 1 is submitted while slot 0 is in flight
+            outs.append(o)
+        for i in range(2):
+            c.stream_wait(i)
+            for k in outs[i]:
+                assert np.array_equal(outs[i][k], want[i][k]), (i, k)
+    finally:
+        c.close()
