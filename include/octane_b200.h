@@ -305,8 +305,10 @@ int octane_pix2uv_band_dev(octane_ctx* ctx, const octane_nav* nav, double t1, do
  * pair run under the solve of the other.  Host buffers must be pinned for the overlap to happen and stay valid
  * until the wait returns.  img*: rows [in0,in1) of octane_band_plan (the whole scene on one GPU); every output:
  * rows [own0,own1).  upix/vpix may both be NULL (the reference writes them only with -pd).  No first guess, no
- * -srsal here.  In banded runs every rank submits the same sequence.  Returns 1 when the sector-moved guard
- * zeroed the navigated outputs. */
+ * -srsal here.  In banded runs every rank submits the same sequence; there a pair's copy-out is enqueued by the NEXT
+ * submit, to start when that pair's solve reaches its finest level (a device-to-host copy in flight slows the
+ * system-scope fences of the short coarse-level iterations), or by octane_stream_wait if no submit followed.
+ * Returns 1 when the sector-moved guard zeroed the navigated outputs. */
 int octane_stream_submit(octane_ctx* ctx, int slot, const float* img1_band, const float* img2_band, const float* cth_own,
                          int nx, int ny, int nc, const octane_nav* nav, double t1, double t2, const octane_params* p,
                          float* upix_own, float* vpix_own, short* U, short* V, short* U_raw, short* V_raw, short* ctp_own);

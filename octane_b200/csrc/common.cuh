@@ -74,14 +74,28 @@ struct P2P {
     unsigned* epoch;              // device [P2P_NPHASE], advanced by the publishing block
 };
 
+// Scope of the fences / release-acquire pairs that order stores into a peer GPU's memory.  System scope is what
+// the PTX memory model requires between two GPUs.  OCTANE_PEER_SCOPE_GPU is a timing experiment only (DESIGN.md
+// section 5: what a system-scope fence costs while a device-to-host copy is in flight); never ship it.
+#ifdef OCTANE_PEER_SCOPE_GPU
+#define OCTANE_FENCE_PEER() __threadfence()
+#define OCTANE_PEER_SCOPE "gpu"
+#else
+#define OCTANE_FENCE_PEER() __threadfence_system()
+#define OCTANE_PEER_SCOPE "sys"
+#endif
+// A thread's stores into a peer GPU's memory (the halo rows of r) are not fenced one by one: every block ends in a
+// barrier (block_sum) followed by ONE system-scope fence of its thread 0 before the ticket (grid_sum_finish), which
+// is cumulative over the stores the barrier ordered before it, and the publishing block releases at system scope.
+// (Per-store fences cost 13 ms of a 1.1 s banded pair while a device-to-host copy was in flight, call 19.)
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
 {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.release." OCTANE_PEER_SCOPE ".global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
 {
     unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire." OCTANE_PEER_SCOPE ".global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_relaxed_sys(double* p, double v)
@@ -157,7 +171,7 @@ __device__ __forceinline__ bool grid_sum_finish(const double (&mine)[NV], double
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < NV; k++) partials[(size_t)k * nblocks + bid] = mine[k];
-        if (sys_fence) __threadfence_system();      // the block stored into a peer GPU's memory
+        if (sys_fence) OCTANE_FENCE_PEER();      // the block stored into a peer GPU's memory
         else __threadfence();
         unsigned t = atomicAdd(ticket, 1u);
         is_last = (t == nblocks - 1);

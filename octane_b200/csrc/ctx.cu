@@ -202,9 +202,16 @@ struct octane_ctx {
     struct StreamSlot {
         char* buf = nullptr;
         size_t bytes = 0;
-        cudaEvent_t in_ready = nullptr, in_free = nullptr, out_ready = nullptr, done = nullptr;
+        cudaEvent_t in_ready = nullptr, in_free = nullptr, out_ready = nullptr, done = nullptr, mid = nullptr;
         bool busy = false;
+        // copy-out of the pair in this slot, not yet enqueued (see flush_copy_out)
+        bool copy_pending = false;
+        int ncopy = 0;
+        void* dst[8] = { nullptr };
+        const void* src[8] = { nullptr };
+        size_t nbytes[8] = { 0 };
     } slot[2];
+    int copy_out_at_finest = -1;          // slot whose pending copy-out run_levels enqueues when the finest level starts
     cudaStream_t h2d_stream = nullptr;
     int copy_prio = 0;
     // host-API staging (device)
@@ -527,6 +534,24 @@ int run_pcg(octane_ctx* c, const Level& L, int level, int solve, int const_wn)
 // ---- coarse-to-fine driver (:487-1210) ----------------------------------------------------
 // Inputs are already in buf.img1/img2 (pitched, rows [in0,in1)) and, with a first guess,
 // buf.uh/vh.  Output: buf.u/v at the finest level.
+// Enqueue the device-to-host copies of the pair in slot k on the copy stream: after that pair's results are ready
+// and, with after_here, not before the point the solve stream has reached now.
+int flush_copy_out(octane_ctx* c, int k, bool after_here)
+{
+    auto& sl = c->slot[k];
+    if (!sl.copy_pending) return OCTANE_OK;
+    if (after_here) {
+        CUDA_OK(cudaEventRecord(sl.mid, c->stream));
+        CUDA_OK(cudaStreamWaitEvent(c->copy_stream, sl.mid, 0));
+    }
+    CUDA_OK(cudaStreamWaitEvent(c->copy_stream, sl.out_ready, 0));
+    for (int i = 0; i < sl.ncopy; i++)
+        CUDA_OK(cudaMemcpyAsync(sl.dst[i], sl.src[i], sl.nbytes[i], cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_OK(cudaEventRecord(sl.done, c->copy_stream));
+    sl.copy_pending = false;
+    return OCTANE_OK;
+}
+
 int run_levels(octane_ctx* c)
 {
     Plan& pl = c->plan;
@@ -543,6 +568,11 @@ int run_levels(octane_ctx* c)
         const bool finest = (k == K - 1);
         float *g1 = finest ? B.img1 : B.g1c, *g2 = finest ? B.img2 : B.g2c;
         const float *hu = nullptr, *hv = nullptr;
+        if (finest && c->copy_out_at_finest >= 0) {               // pipelined dispatcher, banded: see octane_stream_submit
+            int rc = flush_copy_out(c, c->copy_out_at_finest, true);
+            c->copy_out_at_finest = -1;
+            if (rc) return rc;
+        }
         {
             Scope s(c, CAT_PYR, k);
             if (k > 0) {                                          // :498-503
@@ -918,7 +948,7 @@ void octane_ctx_destroy(octane_ctx* c)
     for (auto& sl : c->slot) {
         if (sl.done) cudaEventSynchronize(sl.done);
         if (sl.buf) cudaFree(sl.buf);
-        for (cudaEvent_t e : { sl.in_ready, sl.in_free, sl.out_ready, sl.done }) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : { sl.in_ready, sl.in_free, sl.out_ready, sl.done, sl.mid }) if (e) cudaEventDestroy(e);
     }
     if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamDestroy(c->h2d_stream); }
     if (c->h_its) cudaFreeHost(c->h_its);
@@ -1623,6 +1653,7 @@ int slot_prepare(octane_ctx* c, int k, size_t bytes)
         CUDA_OK(cudaEventCreateWithFlags(&sl.in_free, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&sl.out_ready, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&sl.mid, cudaEventDisableTiming));
     }
     if (bytes > sl.bytes) {
         if (sl.busy) CUDA_OK(cudaEventSynchronize(sl.done));
@@ -1652,13 +1683,24 @@ int octane_stream_submit(octane_ctx* c, int k, const float* img1, const float* i
     const Level& F = c->plan.lv.back();
     const size_t nin = (size_t)F.g.rows * nx, nown = (size_t)(F.own1 - F.own0) * nx;
     const size_t ib = align_up(nin * nc * sizeof(float)), fb = align_up(nown * sizeof(float)), sb = align_up(nown * sizeof(short));
-    rc = slot_prepare(c, k, 2 * ib + 3 * fb + 5 * sb);
-    if (rc) return rc;
     auto& sl = c->slot[k];
     if (sl.busy) {                       // resubmitting a slot implies its previous pair is finished with
+        rc = flush_copy_out(c, k, false);
+        if (rc) return rc;
         CUDA_OK(cudaEventSynchronize(sl.done));
         sl.busy = false;
     }
+    rc = slot_prepare(c, k, 2 * ib + 3 * fb + 5 * sb);
+    if (rc) return rc;
+    // When does the copy-out of a pair run?  On one GPU right after its navigation, under the next pair's solve.
+    // In a banded run the peer-memory exchanges of every PCG iteration end in system-scope fences, and those take
+    // far longer while a device-to-host copy is in flight: the copy-out of the pair in the
+    // OTHER slot is therefore held back until this pair's solve reaches its finest level, where an iteration is
+    // long and the iterations under the copy are few -- not under the hundreds of short coarse-level iterations a
+    // solve starts with.  wait() enqueues it at once if no later submit() has.
+    static const int defer_env = getenv("OCTANE_STREAM_DEFER") ? atoi(getenv("OCTANE_STREAM_DEFER")) : -1;   // developer switch
+    const bool defer = defer_env >= 0 ? defer_env != 0 : c->comm.world > 1;
+    c->copy_out_at_finest = (defer && c->slot[k ^ 1].copy_pending) ? (k ^ 1) : -1;
     char* q = sl.buf;
     float* d_i1 = (float*)q; q += ib;
     float* d_i2 = (float*)q; q += ib;
@@ -1699,17 +1741,20 @@ int octane_stream_submit(octane_ctx* c, int k, const float* img1, const float* i
     if (nrc < 0) return nrc;
     CUDA_OK(cudaEventRecord(sl.out_ready, c->stream));
     // copy-out
-    CUDA_OK(cudaStreamWaitEvent(c->copy_stream, sl.out_ready, 0));
+    sl.ncopy = 0;
+    auto add = [&](void* dst, const void* src, size_t n) { sl.dst[sl.ncopy] = dst; sl.src[sl.ncopy] = src; sl.nbytes[sl.ncopy] = n; sl.ncopy++; };
     short* hs[4] = { U, V, Ur, Vr };
-    for (int i = 0; i < 4 && !(skip & 2); i++)
-        CUDA_OK(cudaMemcpyAsync(hs[i], d_s + i * sstride, nown * sizeof(short), cudaMemcpyDeviceToHost, c->copy_stream));
-    if (p->doCTH) CUDA_OK(cudaMemcpyAsync(ctp, d_s + 4 * sstride, nown * sizeof(short), cudaMemcpyDeviceToHost, c->copy_stream));
-    if (upix && !(skip & 2)) {
-        CUDA_OK(cudaMemcpyAsync(upix, d_u, nown * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
-        CUDA_OK(cudaMemcpyAsync(vpix, d_v, nown * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
-    }
-    CUDA_OK(cudaEventRecord(sl.done, c->copy_stream));
+    for (int i = 0; i < 4 && !(skip & 2); i++) add(hs[i], d_s + i * sstride, nown * sizeof(short));
+    if (p->doCTH) add(ctp, d_s + 4 * sstride, nown * sizeof(short));
+    if (upix && !(skip & 2)) { add(upix, d_u, nown * sizeof(float)); add(vpix, d_v, nown * sizeof(float)); }
+    sl.copy_pending = true;
     sl.busy = true;
+    if (c->copy_out_at_finest >= 0) {    // a solve that never reached run_levels' hook (cannot happen today): do not lose the copy
+        rc = flush_copy_out(c, c->copy_out_at_finest, false);
+        c->copy_out_at_finest = -1;
+        if (rc) return rc;
+    }
+    if (!defer) { rc = flush_copy_out(c, k, false); if (rc) return rc; }
     return nrc;
 }
 
@@ -1719,6 +1764,8 @@ int octane_stream_wait(octane_ctx* c, int k)
     auto& sl = c->slot[k];
     if (!sl.busy) return OCTANE_OK;
     CUDA_OK(cudaSetDevice(c->device));
+    int rc = flush_copy_out(c, k, false);       // not yet enqueued by a later submit(): now
+    if (rc) return rc;
     CUDA_OK(cudaEventSynchronize(sl.done));
     sl.busy = false;
     if (c->comm.world > 1) {

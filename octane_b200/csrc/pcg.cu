@@ -274,8 +274,8 @@ __device__ __forceinline__ void pass2_units(const P1Args& a, float alphak, bool 
             // the band's first / last owned row is the neighbour's halo row: store it there as well
             // (peer memory over NVLink), so the next pass 1 rebuilds p on the halo without an exchange step
             const int j = a.ja + jr;
-            if (j == a.ja && a.b.up_ru) { st4(a.b.up_ru + off, r_u); st4(a.b.up_rv + off, r_v); __threadfence_system(); }
-            if (j == a.jb - 1 && a.b.dn_ru) { st4(a.b.dn_ru + off, r_u); st4(a.b.dn_rv + off, r_v); __threadfence_system(); }
+            if (j == a.ja && a.b.up_ru) { st4(a.b.up_ru + off, r_u); st4(a.b.up_rv + off, r_v); }
+            if (j == a.jb - 1 && a.b.dn_ru) { st4(a.b.dn_ru + off, r_u); st4(a.b.dn_rv + off, r_v); }
         }
         acc[0] += (double)prr;
         acc[1] += (double)prz;

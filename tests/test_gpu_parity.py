@@ -563,3 +563,18 @@ def test_fresh_context_first_call_is_the_pipelined_dispatcher():
                 assert np.array_equal(outs[i][k], want[i][k]), (i, k)
     finally:
         c.close()
+
+
+def test_pipelined_dispatcher_with_deferred_copy_out():
+    """Banded contexts hold a pair's copy-out back until the next pair's solve reaches its finest level.
+    OCTANE_STREAM_DEFER=1 switches that schedule on for a single-GPU context: the two dispatcher tests above must pass
+    unchanged under it (the switch is read once per process, hence the child process)."""
+    import subprocess
+    import sys
+    if os.environ.get("OCTANE_STREAM_DEFER"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, OCTANE_STREAM_DEFER="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "test_pipelined_dispatcher_matches_blocking_calls or test_fresh_context_first_call"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
