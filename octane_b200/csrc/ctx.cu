@@ -607,10 +607,10 @@ int run_levels(octane_ctx* c)
                     CUDA_OK(cudaMemsetAsync(B.v, 0, (size_t)g.plane * sizeof(float), st));
                 }
             }
-            // :587-595 (the third call's y-output is overwritten by the fourth, as in the reference)
+            // :587-595 (the reference's third call also writes d(g2x)/dy into g2xy, which its fourth call overwrites)
             launch_gradient(g1, B.g1x, B.g1y, g, g.jlo(), g.jhi(), nc, st);
             launch_gradient(g2, B.g2x, B.g2y, g, g.jlo(), g.jhi(), nc, st);
-            launch_gradient(B.g2x, B.g2xx, B.g2xy, g, g.jlo(), g.jhi(), nc, st);
+            launch_gradient(B.g2x, B.g2xx, nullptr, g, g.jlo(), g.jhi(), nc, st);     // its y-output would be overwritten next
             launch_gradient(B.g2y, B.g2xy, B.g2yy, g, g.jlo(), g.jhi(), nc, st);
             c->launches += 4;
         }
@@ -1860,7 +1860,7 @@ int octane_stage_build(octane_ctx* c, const float* d_u, const float* d_v, const 
     if (q.first_guess) { if ((rc = copy_in(c, B.uh, d_uh, g, 1))) return rc; if ((rc = copy_in(c, B.vh, d_vh, g, 1))) return rc; }
     launch_gradient(B.img1, B.g1x, B.g1y, g, 0, yi, nc, st);
     launch_gradient(B.img2, B.g2x, B.g2y, g, 0, yi, nc, st);
-    launch_gradient(B.g2x, B.g2xx, B.g2xy, g, 0, yi, nc, st);
+    launch_gradient(B.g2x, B.g2xx, nullptr, g, 0, yi, nc, st);
     launch_gradient(B.g2y, B.g2xy, B.g2yy, g, 0, yi, nc, st);
     LevelFields f;
     f.g1 = B.img1; f.g1x = B.g1x; f.g1y = B.g1y;

@@ -2,6 +2,8 @@
 // bicubic flow prolongation.  Replaces the device functions fill_GK, convh,
 // convv, zoom_out, oct_compgrad_cu, zoom_in, oct_bicubic_cu of
 // src/oct_variational_optical_flow.cu:208-466 (reference tree).
+#include <stdint.h>
+
 #include "kernels.cuh"
 
 namespace octane {
@@ -80,23 +82,102 @@ k_blur_decimate(const float* __restrict__ src, Geom gs, float* __restrict__ dst,
 
 // ---- 4th-order central differences, :411-449 ---------------------------------
 // numerator in double (the literal 8. promotes it), divided by 12.0, stored float.
+__device__ __forceinline__ double grad_num(float p2, float p1, float m1, float m2) { return (-p2 + 8. * p1 - 8. * m1 + m2); }
+
+// x / 12.0, correctly rounded, without the division: y = RN(1/12) has a relative error of 2^-54, so q = RN(x*y) is
+// within one ulp of the quotient, the residual r = x - 12 q is exact in one FMA, and one Markstein correction step
+// returns RN(x / 12) -- the same double the reference's division produces
+// (tests/test_abi_host.py::test_exact_division_shortcuts checks the identity on the CPU).
+__device__ __forceinline__ double div12(double x)
+{
+    const double y = 1.0 / 12.0;
+    const double q = x * y;
+    const double r = fma(-q, 12.0, x);
+    return fma(r, y, q);
+}
+
+// A thread owns 4 consecutive columns and walks GRAD_ROWS rows with the five rows of the y-stencil rolling through
+// registers (every input row is loaded once per 8 output rows, as one 16-byte vector); the two columns either side
+// that the x-stencil needs come from the neighbouring lanes.  Columns at and beyond nx carry the value of column
+// nx - 1, rows are clamped to the image and to the rows the band holds -- the reference's clamp-to-edge taps.
+// gy may be null (the reference's third call: its y-output is overwritten by the fourth).
+#define GRAD_ROWS 8
+template <bool VEC>
+__device__ __forceinline__ float4 grad_row(const float* __restrict__ f, const Geom& g, int i0, int j)
+{
+    const int lo = g.jlo(), hi = g.jhi() - 1;
+    const float* r = f + g.at(0, min(max(clampi(j, g.ny), lo), hi));
+    float4 c;
+    if (i0 + 3 < g.nx) {
+        if (VEC) c = __ldg(reinterpret_cast<const float4*>(r + i0));
+        else { c.x = __ldg(r + i0); c.y = __ldg(r + i0 + 1); c.z = __ldg(r + i0 + 2); c.w = __ldg(r + i0 + 3); }
+    } else {
+        const float e = __ldg(r + g.nx - 1);
+        c.x = i0 < g.nx ? __ldg(r + i0) : e;
+        c.y = i0 + 1 < g.nx ? __ldg(r + i0 + 1) : e;
+        c.z = i0 + 2 < g.nx ? __ldg(r + i0 + 2) : e;
+        c.w = e;
+    }
+    return c;
+}
+
+// VEC: rows start on 16-byte boundaries (every plane of a plan does; the dense arrays of the stage entry point need not)
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_gradient(const float* __restrict__ f, float* __restrict__ gx, float* __restrict__ gy, Geom g,
            int ja, int jb, int nc)
 {
-    const int i = blockIdx.x * 32 + threadIdx.x;
-    const int j = ja + blockIdx.y * 8 + threadIdx.y;
-    if (i >= g.nx || j >= jb) return;
+    const int lane = threadIdx.x;
+    const int i0 = (blockIdx.x * 32 + lane) * 4;
+    const int js = ja + (blockIdx.y * 8 + threadIdx.y) * GRAD_ROWS;
+    if (js >= jb) return;                                  // whole warp: js depends on threadIdx.y only
     const size_t coff = (size_t)blockIdx.z * g.plane;
-    f += coff; gx += coff; gy += coff;
+    f += coff; gx += coff;
+    if (gy) gy += coff;
     const int lo = g.jlo(), hi = g.jhi() - 1;
-    const int jp1 = min(max(clampi(j + 1, g.ny), lo), hi), jp2 = min(max(clampi(j + 2, g.ny), lo), hi);
-    const int jm1 = min(max(clampi(j - 1, g.ny), lo), hi), jm2 = min(max(clampi(j - 2, g.ny), lo), hi);
-    const int ip1 = clampi(i + 1, g.nx), ip2 = clampi(i + 2, g.nx);
-    const int im1 = clampi(i - 1, g.nx), im2 = clampi(i - 2, g.nx);
-    const float* r = f + g.at(0, j);
-    gx[g.at(i, j)] = (-r[ip2] + 8. * r[ip1] - 8. * r[im1] + r[im2]) / 12.0;
-    gy[g.at(i, j)] = (-f[g.at(i, jp2)] + 8. * f[g.at(i, jp1)] - 8. * f[g.at(i, jm1)] + f[g.at(i, jm2)]) / 12.0;
+    float4 w0 = grad_row<VEC>(f, g, i0, js - 2), w1 = grad_row<VEC>(f, g, i0, js - 1), w2 = grad_row<VEC>(f, g, i0, js),
+           w3 = grad_row<VEC>(f, g, i0, js + 1), w4 = grad_row<VEC>(f, g, i0, js + 2);
+    const int je = min(js + GRAD_ROWS, jb);
+    for (int j = js; j < je; j++) {
+        // columns i0-2, i0-1 and i0+4, i0+5 of row j
+        float l2 = __shfl_up_sync(0xffffffffu, w2.z, 1), l1 = __shfl_up_sync(0xffffffffu, w2.w, 1);
+        float r1 = __shfl_down_sync(0xffffffffu, w2.x, 1), r2 = __shfl_down_sync(0xffffffffu, w2.y, 1);
+        if (lane == 0 || lane == 31) {
+            const float* r = f + g.at(0, min(max(clampi(j, g.ny), lo), hi));
+            if (lane == 0) { l2 = __ldg(r + clampi(i0 - 2, g.nx)); l1 = __ldg(r + clampi(i0 - 1, g.nx)); }
+            else { r1 = __ldg(r + clampi(i0 + 4, g.nx)); r2 = __ldg(r + clampi(i0 + 5, g.nx)); }
+        }
+        if (i0 < g.nx) {
+            float4 ox, oy;
+            ox.x = div12(grad_num(w2.z, w2.y, l1, l2));
+            ox.y = div12(grad_num(w2.w, w2.z, w2.x, l1));
+            ox.z = div12(grad_num(r1, w2.w, w2.y, w2.x));
+            ox.w = div12(grad_num(r2, r1, w2.z, w2.y));
+            oy.x = div12(grad_num(w4.x, w3.x, w1.x, w0.x));
+            oy.y = div12(grad_num(w4.y, w3.y, w1.y, w0.y));
+            oy.z = div12(grad_num(w4.z, w3.z, w1.z, w0.z));
+            oy.w = div12(grad_num(w4.w, w3.w, w1.w, w0.w));
+            const size_t o = g.at(i0, j);
+            if (VEC && i0 + 3 < g.nx) {
+                *reinterpret_cast<float4*>(gx + o) = ox;
+                if (gy) *reinterpret_cast<float4*>(gy + o) = oy;
+            } else if (i0 + 3 < g.nx) {
+                gx[o] = ox.x; gx[o + 1] = ox.y; gx[o + 2] = ox.z; gx[o + 3] = ox.w;
+                if (gy) { gy[o] = oy.x; gy[o + 1] = oy.y; gy[o + 2] = oy.z; gy[o + 3] = oy.w; }
+            } else {                                        // last, partial vector of a row: padding is not written
+                gx[o] = ox.x;
+                if (i0 + 1 < g.nx) gx[o + 1] = ox.y;
+                if (i0 + 2 < g.nx) gx[o + 2] = ox.z;
+                if (gy) {
+                    gy[o] = oy.x;
+                    if (i0 + 1 < g.nx) gy[o + 1] = oy.y;
+                    if (i0 + 2 < g.nx) gy[o + 2] = oy.z;
+                }
+            }
+        }
+        w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+        if (j + 1 < je) w4 = grad_row<VEC>(f, g, i0, j + 3);
+    }
 }
 
 // ---- bicubic, :231-309 ---------------------------------------------------------
@@ -131,17 +212,55 @@ __device__ __forceinline__ float bicubic(const float* __restrict__ in, const Geo
 }
 
 // ---- flow prolongation, :453-466 -------------------------------------------------
+// The bicubic of :231-309 interpolates four columns along y and the four results along x.  The y-part of a column
+// depends on the coarse column and the fine row only, so a warp (one fine row, 128 fine columns) evaluates it once
+// per coarse column it touches (about 68 for a factor of 2, into shared memory) instead of four times per pixel:
+// 1.5 instead of 5 cell evaluations and 2 instead of 16 loads per pixel, same operands and same operations per value.
+#define ZOOM_COLS 128          // fine columns per warp
+#define ZOOM_VMAX 144          // coarse columns a warp can hold (ZOOM_COLS / factor + 4, factor >= 1 up to rounding)
+__device__ __forceinline__ float zoom_u(int ii, float factorx) { return (float)((ii / factorx) - (0.5 - 0.5 / factorx)); }
+
 __global__ void __launch_bounds__(256)
 k_zoom_in(const float* __restrict__ flow, Geom gc, float* __restrict__ out, Geom gf, int ja, int jb, float sf)
 {
-    const int ii = blockIdx.x * 32 + threadIdx.x;
-    const int jj = ja + blockIdx.y * 8 + threadIdx.y;
-    if (ii >= gf.nx || jj >= jb) return;
+    __shared__ float V[8][ZOOM_VMAX];
+    const int lane = threadIdx.x, wy = threadIdx.y;
+    const int ibase = blockIdx.x * ZOOM_COLS;
+    const int jj = ja + blockIdx.y * 8 + wy;
+    if (jj >= jb || ibase >= gf.nx) return;                // whole warp
     const float factorx = ((float)gf.nx / gc.nx);
     const float factory = ((float)gf.ny / gc.ny);
-    float i2 = (float)((ii / factorx) - (0.5 - 0.5 / factorx));
-    float j2 = (float)((jj / factory) - (0.5 - 0.5 / factory));
-    out[gf.at(ii, jj)] = bicubic(flow, gc, i2, j2) / sf;
+    const float vv = (float)((jj / factory) - (0.5 - 0.5 / factory));
+    // the warp's coarse columns: the taps (int)(u - 1) .. (int)(u + 2), clamped, are monotone in the fine column
+    const int ilast = min(ibase + ZOOM_COLS, gf.nx) - 1;
+    const int cmin = clampi((int)(zoom_u(ibase, factorx) - 1), gc.nx);
+    const int cmax = clampi((int)(zoom_u(ilast, factorx) + 2), gc.nx);
+    const int ncol = cmax - cmin + 1;
+    if (ncol > ZOOM_VMAX) {                                 // a factor below 1: the direct form
+        for (int ii = ibase + lane; ii <= ilast; ii += 32)
+            out[gf.at(ii, jj)] = bicubic(flow, gc, zoom_u(ii, factorx), vv) / sf;
+        return;
+    }
+    const int y = clampi((int)vv, gc.ny), my = clampi((int)(vv - 1), gc.ny);
+    const int dy = clampi((int)(vv + 1), gc.ny), ddy = clampi((int)(vv + 2), gc.ny);
+    const int ys[4] = { my, y, dy, ddy };
+    const float* rows[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) rows[b] = flow + gc.at(0, min(max(ys[b], gc.jlo()), gc.jhi() - 1));
+    for (int c = lane; c < ncol; c += 32) {
+        float p[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) p[b] = __ldg(rows[b] + cmin + c);
+        V[wy][c] = oct_cell(p, vv - y);
+    }
+    __syncwarp();
+    for (int ii = ibase + lane; ii <= ilast; ii += 32) {
+        const float uu = zoom_u(ii, factorx);
+        const int x = clampi((int)uu, gc.nx), mx = clampi((int)(uu - 1), gc.nx);
+        const int dx = clampi((int)(uu + 1), gc.nx), ddx = clampi((int)(uu + 2), gc.nx);
+        const float v[4] = { V[wy][mx - cmin], V[wy][x - cmin], V[wy][dx - cmin], V[wy][ddx - cmin] };
+        out[gf.at(ii, jj)] = oct_cell(v, uu - x) / sf;
+    }
 }
 
 // ---- dense <-> pitched copies, u += x ---------------------------------------------
@@ -183,15 +302,18 @@ void launch_blur_decimate(const float* src, const Geom& gs, float* dst, const Ge
 void launch_gradient(const float* f, float* gx, float* gy, const Geom& g, int ja, int jb, int nc, cudaStream_t st)
 {
     if (jb <= ja) return;
-    dim3 grid((g.nx + 31) / 32, (jb - ja + 7) / 8, nc), block(32, 8);
-    k_gradient<<<grid, block, 0, st>>>(f, gx, gy, g, ja, jb, nc);
+    dim3 grid((g.nx + 127) / 128, (jb - ja + 8 * GRAD_ROWS - 1) / (8 * GRAD_ROWS), nc), block(32, 8);
+    const bool vec = (g.pitch & 3) == 0 && (g.plane & 3) == 0 &&
+                     (((uintptr_t)f | (uintptr_t)gx | (uintptr_t)gy) & 15) == 0;
+    if (vec) k_gradient<true><<<grid, block, 0, st>>>(f, gx, gy, g, ja, jb, nc);
+    else k_gradient<false><<<grid, block, 0, st>>>(f, gx, gy, g, ja, jb, nc);
 }
 
 void launch_zoom_in(const float* flow, const Geom& gc, float* out, const Geom& gf, int ja, int jb, float sf,
                     cudaStream_t st)
 {
     if (jb <= ja) return;
-    dim3 grid((gf.nx + 31) / 32, (jb - ja + 7) / 8), block(32, 8);
+    dim3 grid((gf.nx + ZOOM_COLS - 1) / ZOOM_COLS, (jb - ja + 7) / 8), block(32, 8);
     k_zoom_in<<<grid, block, 0, st>>>(flow, gc, out, gf, ja, jb, sf);
 }
 

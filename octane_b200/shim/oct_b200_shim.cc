@@ -46,6 +46,13 @@ octane_ctx* g_ctx[64] = { nullptr };
 
 octane_ctx* context_for(int device)
 {
+    // this file was compiled against a header with OCTANE_ABI_VERSION; a library built from another one would
+    // read / write past the structs passed below
+    if (octane_abi_version() != OCTANE_ABI_VERSION) {
+        fprintf(stderr, "octane_b200: liboctane_b200.so has ABI version %d, this shim was compiled for version %d\n",
+                octane_abi_version(), OCTANE_ABI_VERSION);
+        exit(1);
+    }
     const int n = octane_device_count();
     if (n == 0) {
         std::cout << "No gpus available for use, exiting\n";

@@ -767,6 +767,33 @@ long oracle_check_div_const(double a, unsigned long long seed, long n)
     return bad;
 }
 
+/* pyramid.cu: div12 -- the 4th-order difference's numerator (a double built from four floats, :411-449) divided by 12.0
+ * through RN(1/12), one exact residual and one correction step must be the double the division gives.  mode 0: four
+ * floats of arbitrary exponents (wide numerators); mode 1: image-like values of similar size. */
+long oracle_check_div12(unsigned long long seed, long n, int mode)
+{
+    const double y = 1.0 / 12.0;
+    long bad = 0;
+    unsigned long long s = seed ? seed : 88172645463325252ULL;
+    for (long k = 0; k < n; k++) {
+        float v[4];
+        for (int t = 0; t < 4; t++) {
+            s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+            uint32_t b = (uint32_t)(s >> 16);
+            if (mode == 1) b = (b & 0x807fffffu) | ((uint32_t)(120 + (b >> 23) % 12) << 23);   /* 2^-7 .. 2^4 */
+            memcpy(&v[t], &b, 4);
+            if (!(v[t] == v[t]) || isinf(v[t])) v[t] = 1.0f;
+        }
+        const double x = (-v[0] + 8. * v[1] - 8. * v[2] + v[3]);
+        if (isinf(x)) continue;
+        const double q = x * y;
+        const double r = fma(-q, 12.0, x);
+        const double q1 = fma(r, y, q);
+        if (q1 != x / 12.0 && !(fabs(x / 12.0) < 2.3e-308)) bad++;      /* subnormal quotients: floats cannot produce them */
+    }
+    return bad;
+}
+
 /* ---- ingest: octnavcalcuda, src/oct_navcal_cuda.cu:12-98 (host wrapper :100-207) ---------------
  * Calibration constants as oct_navcal_cuda receives them (all float).  cal: 0 RAW, 1 TEMP, 2 REF,
  * 3 BRIT.  lat/lon may be NULL. */

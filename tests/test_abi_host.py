@@ -171,6 +171,11 @@ def test_exact_division_shortcuts(oracle):
     assert L.oracle_check_recip_float(61, 7) == 0
     for a in (5.0, 3.0, 7.3, 0.1, 1e-3, 15.0, 1.0, 2.5, 123.456):
         assert L.oracle_check_div_const(a, 12345, 2_000_000) == 0
+    # pyramid.cu div12: the gradient's double numerator / 12.0 without a division
+    L.oracle_check_div12.argtypes = [C.c_ulonglong, C.c_long, C.c_int]
+    L.oracle_check_div12.restype = C.c_long
+    assert L.oracle_check_div12(777, 3_000_000, 0) == 0
+    assert L.oracle_check_div12(778, 3_000_000, 1) == 0
 
 
 def test_band_table_matches_reference_values():

@@ -145,7 +145,7 @@ def test_stage_blur_decimate(ctx, oracle, shape, factor):
     assert np.abs(got - want).max() <= 1e-6 * 255 * 4
 
 
-@pytest.mark.parametrize("shape", [(96, 80), (257, 131), (33, 17)])
+@pytest.mark.parametrize("shape", [(96, 80), (257, 131), (33, 17), (260, 70), (4, 5), (3, 9), (132, 64)])
 def test_stage_gradient_bit_exact(ctx, oracle, shape):
     import torch
     nx, ny = shape
@@ -157,7 +157,8 @@ def test_stage_gradient_bit_exact(ctx, oracle, shape):
     assert np.array_equal(dgx.cpu().numpy(), gx) and np.array_equal(dgy.cpu().numpy(), gy)
 
 
-@pytest.mark.parametrize("dims", [((63, 63), (125, 125)), ((125, 125), (250, 250)), ((16, 18), (32, 35)), ((40, 30), (81, 59))])
+@pytest.mark.parametrize("dims", [((63, 63), (125, 125)), ((125, 125), (250, 250)), ((16, 18), (32, 35)), ((40, 30), (81, 59)),
+                                  ((150, 20), (300, 41)), ((129, 9), (259, 17)), ((200, 12), (230, 13))])
 def test_stage_zoom_in_bit_exact(ctx, oracle, dims):
     import torch
     (nx, ny), (nxx, nyy) = dims
