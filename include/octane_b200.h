@@ -45,6 +45,13 @@
  *                              src/oct_srsal_cuda.cu:73 (-srsal, called by oct_optical_flow.cc:100-105)
  * Image layout everywhere: row-major float32, index i + nx*j (+ nx*ny*c), i = x
  * (fastest), as the reference (src/oct_variational_optical_flow.cu:316-320).
+ *
+ * Environment variables the library reads (all optional; none changes a result):
+ *   OCTANE_NCCL_LIB       path of libnccl.so.2 when neither the host process nor the loader path has one
+ *   OCTANE_COMM=nccl      banded runs: per-iteration exchanges over NCCL instead of peer memory (and the two-pass kernels)
+ *   OCTANE_STREAM_DEFER   0 / 1: force the copy-out schedule of octane_stream_submit (default: deferred on banded
+ *                         contexts only, see there); used by the tests to run the banded schedule on one GPU
+ *   OCTANE_DUMP_EVENTS    file that receives the per-launch event times of a profiled call (octane_ctx_set_profile)
  */
 #ifndef OCTANE_B200_H
 #define OCTANE_B200_H

@@ -213,7 +213,6 @@ struct octane_ctx {
     } slot[2];
     int copy_out_at_finest = -1;          // slot whose pending copy-out run_levels enqueues when the finest level starts
     cudaStream_t h2d_stream = nullptr;
-    int copy_prio = 0;
     // host-API staging (device)
     char* stage = nullptr;
     size_t stage_bytes = 0;
@@ -911,12 +910,7 @@ int octane_ctx_create(octane_ctx** out, int device)
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_err("cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return OCTANE_ECUDA; }
-    // developer switch (timing experiments): the copy streams at the highest stream priority
-    const bool prio = getenv("OCTANE_COPY_PRIO") && atoi(getenv("OCTANE_COPY_PRIO")) != 0;
-    int plo = 0, phi = 0;
-    cudaDeviceGetStreamPriorityRange(&plo, &phi);
-    c->copy_prio = prio ? phi : 0;
-    if (cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, c->copy_prio) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
         set_err("cudaStreamCreate (copy stream)");
         cudaStreamDestroy(c->stream);
@@ -1647,7 +1641,7 @@ namespace {
 int slot_prepare(octane_ctx* c, int k, size_t bytes)
 {
     auto& sl = c->slot[k];
-    if (!c->h2d_stream) CUDA_OK(cudaStreamCreateWithPriority(&c->h2d_stream, cudaStreamNonBlocking, c->copy_prio));
+    if (!c->h2d_stream) CUDA_OK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     if (!sl.done) {
         CUDA_OK(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&sl.in_free, cudaEventDisableTiming));
@@ -1709,13 +1703,9 @@ int octane_stream_submit(octane_ctx* c, int k, const float* img1, const float* i
     float* d_cth = (float*)q; q += fb;
     short* d_s = (short*)q;
     const size_t sstride = sb / sizeof(short);
-    // developer switch for timing experiments only (results are then stale): 1 = skip copy-in, 2 = skip copy-out
-    static const int skip = getenv("OCTANE_STREAM_SKIP") ? atoi(getenv("OCTANE_STREAM_SKIP")) : 0;
     // copy-in on its own stream: runs under the solve of the pair in the other slot
-    if (!(skip & 1)) {
     CUDA_OK(cudaMemcpyAsync(d_i1, img1, nin * nc * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
     CUDA_OK(cudaMemcpyAsync(d_i2, img2, nin * nc * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
-    }
     if (p->doCTH) CUDA_OK(cudaMemcpyAsync(d_cth, cth, nown * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
     CUDA_OK(cudaEventRecord(sl.in_ready, c->h2d_stream));
     // solve + navigation on the context's stream
@@ -1744,9 +1734,9 @@ int octane_stream_submit(octane_ctx* c, int k, const float* img1, const float* i
     sl.ncopy = 0;
     auto add = [&](void* dst, const void* src, size_t n) { sl.dst[sl.ncopy] = dst; sl.src[sl.ncopy] = src; sl.nbytes[sl.ncopy] = n; sl.ncopy++; };
     short* hs[4] = { U, V, Ur, Vr };
-    for (int i = 0; i < 4 && !(skip & 2); i++) add(hs[i], d_s + i * sstride, nown * sizeof(short));
+    for (int i = 0; i < 4; i++) add(hs[i], d_s + i * sstride, nown * sizeof(short));
     if (p->doCTH) add(ctp, d_s + 4 * sstride, nown * sizeof(short));
-    if (upix && !(skip & 2)) { add(upix, d_u, nown * sizeof(float)); add(vpix, d_v, nown * sizeof(float)); }
+    if (upix) { add(upix, d_u, nown * sizeof(float)); add(vpix, d_v, nown * sizeof(float)); }
     sl.copy_pending = true;
     sl.busy = true;
     if (c->copy_out_at_finest >= 0) {    // a solve that never reached run_levels' hook (cannot happen today): do not lose the copy
