@@ -12,7 +12,7 @@ namespace cdf {
 
 namespace {
 
-constexpr uint32_t NC_DIMENSION = 10, NC_VARIABLE = 11, NC_ATTRIBUTE = 12;
+constexpr uint32_t TAG_DIMENSION = 10, TAG_VARIABLE = 11, TAG_ATTRIBUTE = 12;
 constexpr size_t CHUNK = 1 << 20;     // elements converted per fwrite / fread
 
 uint64_t pad4(uint64_t n) { return (n + 3) & ~(uint64_t)3; }
@@ -50,7 +50,7 @@ struct Buf {                          // header assembly
     void att_list(const std::vector<Att>& v)
     {
         if (v.empty()) { u32(0); u32(0); return; }
-        u32(NC_ATTRIBUTE);
+        u32(TAG_ATTRIBUTE);
         u32((uint32_t)v.size());
         for (auto& a : v) att(a);
     }
@@ -153,7 +153,7 @@ int Writer::enddef()
         h.u32(0);                                                                       // no records
         if (dims_.empty()) { h.u32(0); h.u32(0); }
         else {
-            h.u32(NC_DIMENSION); h.u32((uint32_t)dims_.size());
+            h.u32(TAG_DIMENSION); h.u32((uint32_t)dims_.size());
             for (auto& d : dims_) {
                 if (d.len > 0xffffffffull) { err_ = "dimension too long for the classic format"; return -1; }
                 h.name(d.name); h.u32((uint32_t)d.len);
@@ -162,7 +162,7 @@ int Writer::enddef()
         h.u32(0); h.u32(0);                                                             // no global attributes
         if (vars_.empty()) { h.u32(0); h.u32(0); }
         else {
-            h.u32(NC_VARIABLE); h.u32((uint32_t)vars_.size());
+            h.u32(TAG_VARIABLE); h.u32((uint32_t)vars_.size());
             uint64_t off = pad4(hdr);
             for (auto& v : vars_) {
                 h.name(v.name);
@@ -255,7 +255,7 @@ struct Cursor {
         const uint32_t tag = u32(), n = u32();
         if (!ok) return false;
         if (tag == 0 && n == 0) return true;
-        if (tag != NC_ATTRIBUTE) return false;
+        if (tag != TAG_ATTRIBUTE) return false;
         for (uint32_t i = 0; i < n && ok; i++) {
             Att a;
             a.name = name();
@@ -279,10 +279,118 @@ struct Cursor {
 
 Reader::~Reader() { close(); }
 
+#ifdef OCTANE_HAVE_NETCDF
+}  // namespace cdf
+#include <netcdf.h>
+namespace cdf {
+bool has_netcdf4() { return true; }
+
+// NetCDF-4 input through the netCDF C library (what the reference's netcdf-cxx4 calls end in,
+// src/oct_fileread.cc:71-263): the header is mirrored into the same Dim / Var / Att records the classic parser
+// fills, so the callers do not know which container they read.  Unsigned and 64-bit attribute types are kept as the
+// next wider classic type; string-typed attributes and user-defined types are skipped (the OCTANE readers use neither).
+static int classic_type(int t)
+{
+    switch (t) {
+    case NC_BYTE: case NC_UBYTE: return BYTE;
+    case NC_CHAR: return CHAR;
+    case NC_SHORT: return SHORT;
+    case NC_USHORT: case NC_INT: return INT;
+    case NC_FLOAT: return FLOAT;
+    case NC_UINT: case NC_INT64: case NC_UINT64: case NC_DOUBLE: return DOUBLE;
+    default: return 0;
+    }
+}
+
+static bool read_atts(int ncid, int varid, int natts, std::vector<Att>& out)
+{
+    for (int k = 0; k < natts; k++) {
+        char name[NC_MAX_NAME + 1];
+        nc_type t;
+        size_t len = 0;
+        if (nc_inq_attname(ncid, varid, k, name) != NC_NOERR || nc_inq_att(ncid, varid, name, &t, &len) != NC_NOERR) return false;
+        Att a;
+        a.name = name;
+        a.type = classic_type(t);
+        if (a.type == 0) continue;
+        a.raw.resize(len * type_size(a.type));
+        int rc = NC_NOERR;
+        if (len > 0) switch (a.type) {
+        case CHAR:   rc = nc_get_att_text(ncid, varid, name, (char*)a.raw.data()); break;
+        case BYTE:   rc = nc_get_att_schar(ncid, varid, name, (signed char*)a.raw.data()); break;
+        case SHORT:  rc = nc_get_att_short(ncid, varid, name, (short*)a.raw.data()); break;
+        case INT:    rc = nc_get_att_int(ncid, varid, name, (int*)a.raw.data()); break;
+        case FLOAT:  rc = nc_get_att_float(ncid, varid, name, (float*)a.raw.data()); break;
+        case DOUBLE: rc = nc_get_att_double(ncid, varid, name, (double*)a.raw.data()); break;
+        }
+        if (rc != NC_NOERR && rc != NC_ERANGE) return false;
+        out.push_back(a);
+    }
+    return true;
+}
+
+int Reader::open_nc4(const std::string& path)
+{
+    int ncid = -1, rc = nc_open(path.c_str(), NC_NOWRITE, &ncid);
+    if (rc != NC_NOERR) { err_ = path + ": " + nc_strerror(rc); return -1; }
+    ncid_ = ncid;
+    int ndims = 0, nvars = 0, ngatts = 0, unlim = -1;
+    if (nc_inq(ncid, &ndims, &nvars, &ngatts, &unlim) != NC_NOERR) { err_ = path + ": nc_inq failed"; return -1; }
+    for (int d = 0; d < ndims; d++) {
+        char name[NC_MAX_NAME + 1];
+        size_t len = 0;
+        if (nc_inq_dim(ncid, d, name, &len) != NC_NOERR) { err_ = path + ": nc_inq_dim failed"; return -1; }
+        Dim dm; dm.name = name; dm.len = len;
+        dims_.push_back(dm);
+    }
+    if (!read_atts(ncid, NC_GLOBAL, ngatts, gatts_)) { err_ = path + ": cannot read the global attributes"; return -1; }
+    for (int k = 0; k < nvars; k++) {
+        char name[NC_MAX_NAME + 1];
+        nc_type t;
+        int nd = 0, natts = 0, dimids[NC_MAX_VAR_DIMS];
+        if (nc_inq_var(ncid, k, name, &t, &nd, dimids, &natts) != NC_NOERR) { err_ = path + ": nc_inq_var failed"; return -1; }
+        Var v;
+        v.name = name;
+        v.type = classic_type(t);
+        if (v.type == 0 || v.type == CHAR) continue;      // string / user-defined / text variables: not read by OCTANE
+        v.ncvarid = k;
+        v.nelems = 1;
+        for (int i = 0; i < nd; i++) {
+            if (dimids[i] < 0 || dimids[i] >= (int)dims_.size()) { err_ = path + ": bad dimension id"; return -1; }
+            v.dimids.push_back(dimids[i]);
+            const uint64_t len = dims_[dimids[i]].len;
+            if (len != 0 && v.nelems > UINT64_MAX / len) { err_ = path + ": variable " + v.name + " is too large"; return -1; }
+            v.nelems *= len;
+        }
+        if (!read_atts(ncid, k, natts, v.atts)) { err_ = path + ": cannot read the attributes of " + v.name; return -1; }
+        vars_.push_back(v);
+    }
+    return 0;
+}
+
+static int nc_get(int ncid, int varid, short* out) { return nc_get_var_short(ncid, varid, out); }
+static int nc_get(int ncid, int varid, int* out) { return nc_get_var_int(ncid, varid, out); }
+static int nc_get(int ncid, int varid, float* out) { return nc_get_var_float(ncid, varid, out); }
+static int nc_get(int ncid, int varid, double* out) { return nc_get_var_double(ncid, varid, out); }
+#define OCTANE_NC_GET(ncid, v, out)                                                              \
+    do {                                                                                         \
+        const int rc_ = nc_get(ncid, (v)->ncvarid, out);   /* NC_ERANGE: a value outside T, as a C cast would give */ \
+        if (rc_ != NC_NOERR && rc_ != NC_ERANGE) { err_ = "read of " + (v)->name + ": " + nc_strerror(rc_); return -1; } \
+        return 0;                                                                                \
+    } while (0)
+static void nc_close_id(int ncid) { nc_close(ncid); }
+#else
+bool has_netcdf4() { return false; }
+int Reader::open_nc4(const std::string& path) { err_ = path + ": built without the netCDF library"; return -1; }
+static void nc_close_id(int) {}
+#endif
+
 void Reader::close()
 {
     if (fp_) fclose((FILE*)fp_);
     fp_ = nullptr;
+    if (ncid_ >= 0) nc_close_id(ncid_);
+    ncid_ = -1;
 }
 
 int Reader::open(const std::string& path)
@@ -295,7 +403,9 @@ int Reader::open(const std::string& path)
     unsigned char magic[4];
     if (fread(magic, 1, 4, f) != 4) { err_ = path + ": empty file"; return -1; }
     if (magic[0] == 0x89 && magic[1] == 'H' && magic[2] == 'D' && magic[3] == 'F') {
-        err_ = path + ": NetCDF-4/HDF5 container; this build reads the classic format only (convert with `nccopy -k cdf2`)";
+        if (has_netcdf4()) { close(); return open_nc4(path); }
+        err_ = path + ": NetCDF-4/HDF5 container; this build reads the classic format only (convert with `nccopy -k cdf2`, "
+                      "or rebuild with the netCDF C library present)";
         return -1;
     }
     if (magic[0] != 'C' || magic[1] != 'D' || magic[2] != 'F' || (magic[3] != 1 && magic[3] != 2)) {
@@ -306,12 +416,12 @@ int Reader::open(const std::string& path)
     Cursor c{ f };
     c.u32();                                            // numrecs (record variables unsupported)
     uint32_t tag = c.u32(), n = c.u32();
-    if (tag == NC_DIMENSION) {
+    if (tag == TAG_DIMENSION) {
         for (uint32_t i = 0; i < n && c.ok; i++) { Dim d; d.name = c.name(); d.len = c.u32(); dims_.push_back(d); }
     } else if (!(tag == 0 && n == 0)) { err_ = path + ": malformed dimension list"; return -1; }
     if (!c.att_list(gatts_)) { err_ = path + ": malformed global attributes"; return -1; }
     tag = c.u32(); n = c.u32();
-    if (tag == NC_VARIABLE) {
+    if (tag == TAG_VARIABLE) {
         for (uint32_t i = 0; i < n && c.ok; i++) {
             Var v;
             v.name = c.name();
@@ -362,6 +472,9 @@ const Var* Reader::var(const std::string& name) const
 
 template <class T> int Reader::get_as(const Var* v, T* out)
 {
+#ifdef OCTANE_HAVE_NETCDF
+    if (ncid_ >= 0 && v && v->ncvarid >= 0) OCTANE_NC_GET(ncid_, v, out);
+#endif
     if (!fp_ || !v) { err_ = "get: no such variable"; return -1; }
     FILE* f = (FILE*)fp_;
     if (fseeko(f, (off_t)v->begin, SEEK_SET) != 0) { err_ = "seek failed"; return -1; }

@@ -6,6 +6,11 @@
 // attributes, variables with attributes, then the fixed-size variable data).  Only what the
 // OCTANE files need: fixed dimensions (no record variables), types byte/char/short/int/float/
 // double, scalar and n-d variables.
+//
+// Operational GOES-R L1b / CLAVR-x files are NetCDF-4 (HDF5 container).  When the build finds the netCDF C library
+// (csrc/Makefile: `nc-config`, or NETCDF_CFLAGS / NETCDF_LIBS) it defines OCTANE_HAVE_NETCDF and the Reader opens such
+// files through it behind the same interface (cdf.cc: open_nc4); without the library the Reader reports what to do
+// (`nccopy -k cdf2`).  The Writer always produces the classic container, which every netCDF tool reads.
 #pragma once
 #include <stdint.h>
 
@@ -39,6 +44,7 @@ struct Var {
     std::vector<Att> atts;
     uint64_t begin = 0;                 // file offset of the data (filled by the reader / by File::enddef)
     uint64_t nelems = 1;
+    int ncvarid = -1;                   // variable id in the netCDF library (OCTANE_HAVE_NETCDF builds, NetCDF-4 input)
     const Att* att(const std::string& n) const;
 };
 
@@ -90,7 +96,12 @@ private:
     std::vector<Att> gatts_;
     void* fp_ = nullptr;
     int version_ = 1;
+    int ncid_ = -1;                     // >= 0: the file is open through the netCDF library (see open_nc4)
+    int open_nc4(const std::string& path);
     std::string err_;
 };
+
+// true when this build links the netCDF C library and can therefore read NetCDF-4 / HDF5 files as well
+bool has_netcdf4();
 
 }  // namespace cdf

@@ -316,3 +316,43 @@ def test_cli_projected_grids_end_to_end(tmp_path, ctx, kind):
         assert np.array_equal(v["U"][:], want["uVal"].astype(np.float64)) and np.array_equal(v["V"][:], want["vVal"].astype(np.float64))
     assert np.abs(want["uPix"]).max() > 0.2
     f.close()
+
+
+def test_netcdf4_backend_against_a_stub_library(tmp_path):
+    """Operational GOES-R L1b files are NetCDF-4 / HDF5.  The image has no netCDF library, so the library backend of
+    cdf::Reader (csrc/cdf.cc, OCTANE_HAVE_NETCDF; selected by csrc/Makefile when `nc-config` is found) is compiled against
+    the declarations in tests/stubs/netcdf.h and run against tests/stubs/fake_netcdf.c, a table-driven stand-in that
+    serves one GOES-shaped dataset: (1) the Reader mirrors dimensions, variables and attributes (unsigned and 64-bit
+    types widened, string types skipped) and converts on read; (2) the `octane` program built that way reads two files
+    that carry the HDF5 signature and writes the reference's schema (dry run, no GPU)."""
+    from scipy.io import netcdf_file
+    tmp = str(tmp_path)
+    stubs = os.path.join(ROOT, "tests", "stubs")
+    csrc = os.path.join(ROOT, "octane_b200", "csrc")
+    cxx = ["g++", "-O2", "-std=c++17", "-Wall", "-D_FILE_OFFSET_BITS=64", "-I", stubs]
+    subprocess.check_call(cxx + ["-DOCTANE_HAVE_NETCDF", "-c", "-o", f"{tmp}/cdf_nc.o", os.path.join(csrc, "cdf.cc")])
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-I", stubs, "-c", "-o", f"{tmp}/fake_nc.o", os.path.join(stubs, "fake_netcdf.c")])
+    subprocess.check_call(cxx + ["-o", f"{tmp}/check", os.path.join(stubs, "nc4_reader_check.cc"), f"{tmp}/cdf_nc.o", f"{tmp}/fake_nc.o"])
+    r = subprocess.run([f"{tmp}/check", f"{tmp}/probe.nc"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout + r.stderr
+    lib = os.path.join(ROOT, "octane_b200", "lib")
+    subprocess.check_call(cxx + ["-o", f"{tmp}/octane_nc4", os.path.join(ROOT, "octane_b200", "cli", "octane_main.cc"), f"{tmp}/cdf_nc.o",
+                                 f"{tmp}/fake_nc.o", "-L", lib, "-loctane_b200", f"-Wl,-rpath,{lib}"])
+    for name in ("file1.nc", "file2.nc"):
+        open(os.path.join(tmp, name), "wb").write(b"\x89HDF\r\n\x1a\n")
+    r = subprocess.run([f"{tmp}/octane_nc4", "-i1", f"{tmp}/file1.nc", "-i2", f"{tmp}/file2.nc", "-o", tmp + "/", "-dry_run"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    f = netcdf_file(os.path.join(tmp, "outfile.nc"), "r", mmap=False)
+    assert list(f.dimensions.items()) == [("x", 8), ("y", 6)]
+    v = f.variables
+    assert np.array_equal(v["x"][:], np.arange(8)) and np.array_equal(v["y"][:], np.arange(10, 16))
+    assert v["Rad"][:].shape == (6, 8) and list(v["Rad"][:][3]) == list(range(4095, 4087, -1)) and int(v["Rad"][:][5, 7]) == 2047
+    assert float(v["x"].scale_factor) == np.float32(5.6e-05) and float(v["y"].add_offset) == np.float32(0.128212)
+    assert float(v["t"].getValue()) == 7.123456789e8 and float(v["optical_flow_settings"].dt_seconds) == 600.0
+    assert float(v["goes_imager_projection"].longitude_of_projection_origin) == -75.0
+    assert abs(float(v["planck_fk1"].getValue()) - 202263.0) < 1e-2 and abs(float(v["kappa0"].getValue()) - 0.0123) < 1e-7
+    f.close()
+    # the shipped binary (no library in this image) still says what to do with such a file
+    r = run("-i1", f"{tmp}/file1.nc", "-i2", f"{tmp}/file2.nc", "-dry_run", check=False)
+    assert r.returncode == 1 and "classic format only" in r.stderr
